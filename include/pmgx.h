@@ -1,0 +1,279 @@
+/* pmgx.h -- C ABI of the B200-native p-multigrid hot path (drop-in boundary).
+ *
+ * Every entry point replaces one piece of the reference's header-only C++
+ * operator API (Wells-Group/pmg-dolfinx, paths relative to the reference root);
+ * the reference interface each one stands in for is cited next to it.  The C++
+ * shim include/pmgx/dolfinx_acc_compat.hpp re-creates the reference's class
+ * names and method signatures on top of these functions.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a PMGX_ERR_* code otherwise;
+ *     pmgx_last_error_string() describes the last failure of the calling thread;
+ *   - pointer arguments are DEVICE pointers unless the name ends in _h (host);
+ *   - vectors follow the reference layout: owned entries [0, n_owned) first,
+ *     ghosts after (src/vector.hpp:86,213-225); all scalars are FP64, indices
+ *     int32, BC markers int8;
+ *   - caller arrays handed to *_create are borrowed for the handle's lifetime
+ *     unless stated otherwise; *_destroy frees everything the handle owns;
+ *   - all device work is enqueued on the context's compute stream and is
+ *     asynchronous w.r.t. the host unless a host scalar is returned;
+ *   - there is NO CPU fallback: every compute entry point fails with
+ *     PMGX_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef PMGX_H
+#define PMGX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMGX_OK 0
+#define PMGX_ERR_ARG 1
+#define PMGX_ERR_CUDA 2
+#define PMGX_ERR_NCCL 3
+#define PMGX_ERR_NUMERIC 4
+#define PMGX_ERR_UNSUPPORTED 5
+
+#define PMGX_MAX_DEGREE 8
+#define PMGX_NCCL_ID_BYTES 128
+
+typedef struct pmgx_ctx pmgx_ctx;
+typedef struct pmgx_halo pmgx_halo;
+typedef struct pmgx_operator pmgx_operator;
+typedef struct pmgx_cheb pmgx_cheb;
+typedef struct pmgx_cg pmgx_cg;
+typedef struct pmgx_interp pmgx_interp;
+typedef struct pmgx_coarse pmgx_coarse;
+typedef struct pmgx_vcycle pmgx_vcycle;
+typedef struct pmgx_boxmesh pmgx_boxmesh;
+
+/* ------------------------------------------------------------------ misc -- */
+const char* pmgx_last_error_string(void);
+int pmgx_version(void);
+
+/* 1-D GLL tables the reference takes from Basix (src/laplacian.hpp:299-317,
+ * src/precompute.hpp:255-271, src/interpolate.hpp:118).  Host, no GPU needed.
+ *   points_h[n], weights_h[n] on [0,1]; dphi_h[n*n] row = quadrature point;
+ *   interp_h[(pf+1)*(pc+1)] = l^c_ic(x^f_if). n = degree+1. Any pointer may be NULL. */
+int pmgx_gll_tables(int degree, double* points_h, double* weights_h, double* dphi_h);
+int pmgx_gll_interp_1d(int degree_coarse, int degree_fine, double* interp_h);
+
+/* Eigenvalues of a symmetric tridiagonal matrix, QL with implicit shifts
+ * (replaces tqli, src/cg.hpp:15-84).  d_h[n] in/out, e_h[n] in (destroyed). */
+int pmgx_tqli(double* d_h, double* e_h, int n);
+
+/* --------------------------------------------------------------- context -- */
+/* One context per GPU / rank (replaces "one MPI rank per GPU",
+ * examples/pmg/select_gpu.sh + MPI_COMM_WORLD).  nccl_id_h: PMGX_NCCL_ID_BYTES
+ * from pmgx_nccl_unique_id() on rank 0 and broadcast by the launcher (torchrun /
+ * torch.distributed, threads, ...); NULL iff nranks == 1. */
+int pmgx_nccl_unique_id(void* id_h);
+int pmgx_ctx_create(int device, int rank, int nranks, const void* nccl_id_h, pmgx_ctx** out);
+int pmgx_ctx_destroy(pmgx_ctx* ctx);
+int pmgx_ctx_sync(pmgx_ctx* ctx);                 /* device_synchronize, src/util.hpp:51-58 */
+void* pmgx_ctx_stream(pmgx_ctx* ctx);             /* cudaStream_t of the compute stream */
+int pmgx_ctx_rank(pmgx_ctx* ctx);
+int pmgx_ctx_nranks(pmgx_ctx* ctx);
+/* number of kernels launched by this library on ctx since creation (bench "gpu_launches") */
+long long pmgx_ctx_launch_count(pmgx_ctx* ctx);
+
+/* ------------------------------------------------------------------ halo -- */
+/* Owner->ghost forward scatter plan (replaces dolfinx::common::Scatterer held by
+ * acc::Vector, src/vector.hpp:83-95).  send_idx_h: owned local indices grouped by
+ * destination rank (Scatterer::local_indices); recv_idx_h: ghost slot (0-based in
+ * the ghost block) of each received value grouped by source rank
+ * (Scatterer::remote_indices).  The index arrays are copied. */
+int pmgx_halo_create(pmgx_ctx* ctx, int n_owned, int n_ghost,
+                     int n_send_nbr, const int* send_ranks_h, const int* send_offsets_h,
+                     const int32_t* send_idx_h,
+                     int n_recv_nbr, const int* recv_ranks_h, const int* recv_offsets_h,
+                     const int32_t* recv_idx_h, pmgx_halo** out);
+int pmgx_halo_destroy(pmgx_halo* h);
+/* Vector::scatter_fwd_begin / scatter_fwd_end (src/vector.hpp:186-238): pack kernel +
+ * grouped ncclSend/ncclRecv on the comm stream, then unpack; the compute stream only
+ * waits in _end. */
+int pmgx_halo_fwd_begin(pmgx_halo* h, double* x);
+int pmgx_halo_fwd_end(pmgx_halo* h, double* x);
+/* Vector::scatter_rev (src/vector.hpp:249-294): ghost -> owner accumulate. */
+int pmgx_halo_rev(pmgx_halo* h, double* x);
+/* stand-alone gather/scatter kernels: pack / unpack / unpack_add, src/vector.hpp:24-55 */
+int pmgx_pack(pmgx_ctx* ctx, int n, const int32_t* idx, const double* in, double* out);
+int pmgx_unpack(pmgx_ctx* ctx, int n, const int32_t* idx, const double* in, double* out);
+int pmgx_unpack_add(pmgx_ctx* ctx, int n, const int32_t* idx, const double* in, double* out);
+
+/* ---------------------------------------------------------- vector kernels -- */
+/* Free functions of dolfinx::acc (src/vector.hpp:333-454) on raw device arrays. */
+int pmgx_vec_set(pmgx_ctx* ctx, double* x, long long n, double v);                 /* Vector::set :109 */
+int pmgx_vec_copy(pmgx_ctx* ctx, double* a, const double* b, long long n);         /* copy :423 */
+int pmgx_vec_axpy(pmgx_ctx* ctx, double* r, double alpha, const double* x,
+                  const double* y, long long n);                                   /* axpy :397 r=alpha*x+y */
+int pmgx_vec_scale(pmgx_ctx* ctx, double* r, double alpha, long long n);           /* scale :412 */
+int pmgx_vec_pointwise_mult(pmgx_ctx* ctx, double* w, const double* x,
+                            const double* y, long long n);                         /* pointwise_mult :437 */
+int pmgx_vec_mask_bc(pmgx_ctx* ctx, double* b, const int8_t* bc, long long n);     /* b*=(1-bc) pmg.hpp:100-103 */
+/* inner_product / squared_norm / norm (src/vector.hpp:333-390): local reduction over the
+ * n owned entries + all-reduce over ranks; result returned on the host (blocking). */
+int pmgx_vec_dot(pmgx_ctx* ctx, const double* a, const double* b, long long n, double* result_h);
+int pmgx_vec_norm(pmgx_ctx* ctx, const double* a, long long n, int linf, double* result_h);
+
+/* -------------------------------------------------- matrix-free Laplacian -- */
+#define PMGX_LAP_DEFAULT 0
+#define PMGX_LAP_LITERAL_DETJ 1   /* reproduce detJ of src/laplacian.hpp:97 verbatim (quirk Q17) */
+#define PMGX_LAP_NO_DIAG 2        /* skip the matrix-free diagonal at create */
+
+/* MatFreeLaplacian ctor (src/laplacian.hpp:289-349).  dofmap[n_cells][(P+1)^3],
+ * xgeom[n_points][3], geom_dofmap[n_cells][8] (tensor-product vertex order),
+ * kappa[n_cells] (read on every apply, like cell_constants :230), lcells_h/bcells_h:
+ * host lists (src/mesh.hpp:105-143), bc_marker[n_owned+n_ghost].  The 1-D GLL table,
+ * the trilinear geometry table and the weights (dphi_geometry / G_weights arguments of
+ * the reference) are generated internally.  dofmap and bc_marker are snapshotted into
+ * an internal BC-encoded copy in launch order; G is owned (reference :512). halo may be
+ * NULL (single rank). */
+int pmgx_laplacian_create(pmgx_ctx* ctx, int degree, int n_cells, const int32_t* dofmap,
+                          const double* xgeom, int n_points, const int32_t* geom_dofmap,
+                          const double* kappa, const int32_t* lcells_h, int n_lcells,
+                          const int32_t* bcells_h, int n_bcells, const int8_t* bc_marker,
+                          int n_owned, int n_ghost, pmgx_halo* halo, int flags,
+                          pmgx_operator** out);
+/* Geometry factors in the reference layout G[n_list][nq][6] (src/laplacian.hpp:99-111), list
+ * order = lcells then bcells (:329-336); for parity tests against geometry_computation. */
+int pmgx_laplacian_get_G(pmgx_operator* op, double* G_out);
+
+/* ------------------------------------------------------------- CSR operator -- */
+/* MatrixOperator (src/csr.hpp:57-131): row_ptr[n_rows+1], off_diag_offset[n_rows] (first
+ * ghost-column entry of each row), cols, values -- HOST arrays, copied.  Columns >= n_owned
+ * address ghosts.  diag^-1 is extracted like src/csr.hpp:101-112. */
+int pmgx_csr_create(pmgx_ctx* ctx, int n_rows, int n_ghost, const int32_t* row_ptr_h,
+                    const int32_t* off_diag_offset_h, const int32_t* cols_h,
+                    const double* values_h, pmgx_halo* halo, pmgx_operator** out);
+/* Assemble the CSR matrix of a matrix-free Laplacian (BC rows/cols zero, diagonal 1:
+ * fem::assemble_matrix + set_diagonal, src/csr.hpp:76-86); rows = owned dofs. Intended for
+ * the coarse P1 level (north_star item 5). */
+int pmgx_csr_from_laplacian(pmgx_operator* lap, pmgx_operator** out);
+long long pmgx_csr_nnz(pmgx_operator* op);                      /* MatrixOperator::nnz :279 */
+int pmgx_csr_get(pmgx_operator* op, int32_t* row_ptr_h, int32_t* cols_h, double* values_h);
+
+/* --------------------------------------------------------- generic operator -- */
+/* Operator::operator()(Vector& in, Vector& out): y = A x, incl. the zero fill and the
+ * forward halo update of x overlapped with the interior cells / owned columns
+ * (src/laplacian.hpp:462-482,373-460; src/csr.hpp:220-273). x's ghost block is refreshed. */
+int pmgx_operator_apply(pmgx_operator* op, double* x, double* y);
+/* get_diag_inverse / set_diag_inverse (src/laplacian.hpp:484-495, src/csr.hpp:205-209):
+ * n_owned values. */
+int pmgx_operator_get_diag_inverse(pmgx_operator* op, double* out);
+int pmgx_operator_set_diag_inverse(pmgx_operator* op, const double* in);
+int pmgx_operator_n_owned(pmgx_operator* op);
+int pmgx_operator_n_ghost(pmgx_operator* op);
+int pmgx_operator_destroy(pmgx_operator* op);
+
+/* ---------------------------------------------------------------- Chebyshev -- */
+/* acc::Chebyshev (src/chebyshev.hpp:25-91): 4th-kind, Jacobi; only eig_max is used (:51). */
+int pmgx_cheb_create(pmgx_ctx* ctx, int n_owned, int n_ghost, double eig_min, double eig_max,
+                     pmgx_cheb** out);
+int pmgx_cheb_set_max_iterations(pmgx_cheb* s, int max_iter);
+/* solve(A, x, b, verbose): resid_hist_h (max_iter+1 entries, may be NULL) receives the
+ * UNPRECONDITIONED residual norms the reference prints when verbose (:59-63,85-89). */
+int pmgx_cheb_solve(pmgx_cheb* s, pmgx_operator* A, double* x, const double* b,
+                    double* resid_hist_h);
+int pmgx_cheb_residual(pmgx_cheb* s, pmgx_operator* A, double* x, const double* b,
+                       double* rnorm_h);                                   /* :37-43 */
+int pmgx_cheb_destroy(pmgx_cheb* s);
+
+/* ----------------------------------------------------------------------- CG -- */
+/* acc::CGSolver (src/cg.hpp:99-222). */
+int pmgx_cg_create(pmgx_ctx* ctx, int n_owned, int n_ghost, pmgx_cg** out);
+int pmgx_cg_set_max_iterations(pmgx_cg* s, int max_iter);
+int pmgx_cg_set_tolerance(pmgx_cg* s, double rtol);
+int pmgx_cg_store_coefficients(pmgx_cg* s, int on);
+/* solve -> iteration count in *iters_h (the reference's return value). */
+int pmgx_cg_solve(pmgx_cg* s, pmgx_operator* A, double* x, const double* b, int* iters_h);
+/* alphas()/betas()/residual history as stored by the reference (:213-218); returns count. */
+int pmgx_cg_num_coefficients(pmgx_cg* s);
+int pmgx_cg_get_coefficients(pmgx_cg* s, double* alphas_h, double* betas_h, double* residuals_h);
+/* every iteration's r.M^-1 r (also the un-stored last one) and rnorm0, for parity tests */
+int pmgx_cg_get_history(pmgx_cg* s, double* rnorm0_h, double* rnorms_h, int* n_h);
+/* compute_eigenvalues (:121-142): sorted Lanczos estimates, eig_h[num_coefficients]. */
+int pmgx_cg_compute_eigenvalues(pmgx_cg* s, double* eig_h);
+int pmgx_cg_destroy(pmgx_cg* s);
+
+/* ------------------------------------------------------------- p-transfer -- */
+/* Interpolator (src/interpolate.hpp:93-181): coarse degree Q1 -> fine degree Q2 on the same
+ * cells. dofmaps are device arrays [n_cells][(P+1)^3]; lcells_h/bcells_h host lists;
+ * halo_c / halo_f: forward-scatter plans of the coarse / fine vectors (may be NULL). */
+int pmgx_interp_create(pmgx_ctx* ctx, int degree_coarse, int degree_fine, int n_cells,
+                       const int32_t* dofmap_coarse, const int32_t* dofmap_fine,
+                       int n_coarse_total, int n_fine_total,
+                       const int32_t* lcells_h, int n_lcells, const int32_t* bcells_h,
+                       int n_bcells, pmgx_halo* halo_c, pmgx_halo* halo_f, pmgx_interp** out);
+int pmgx_interp_prolong(pmgx_interp* it, double* coarse, double* fine);   /* interpolate :185-239 */
+int pmgx_interp_restrict(pmgx_interp* it, double* fine, double* coarse);  /* reverse_interpolate :245-303 */
+int pmgx_interp_destroy(pmgx_interp* it);
+
+/* ------------------------------------------------------------ coarse solver -- */
+/* CoarseSolverType::solve(x, b) (src/amg.hpp:67-113; PETSc CG + BoomerAMG there): here
+ * Jacobi-PCG on the assembled CSR operator (north_star item 5), <= max_iter iterations,
+ * relative tolerance rtol on sqrt(r.M^-1 r). */
+int pmgx_coarse_create(pmgx_ctx* ctx, pmgx_operator* A_csr, int max_iter, double rtol,
+                       pmgx_coarse** out);
+int pmgx_coarse_solve(pmgx_coarse* cs, double* x, const double* b, int* iters_h);
+int pmgx_coarse_destroy(pmgx_coarse* cs);
+
+/* ------------------------------------------------------------------ V-cycle -- */
+/* MultigridPreconditioner (src/pmg.hpp:22-155). Level 0 is the coarsest.  ops[n_levels],
+ * smoothers[n_levels], interps[n_levels-1] (interps[i]: level i -> i+1), bc_markers[n_levels]
+ * device int8 arrays (the reference takes only level 0's, :22-24; quirk Q9), coarse may be
+ * NULL (then smoothers[0] is used, :106-109). */
+#define PMGX_VC_DEFAULT 0
+#define PMGX_VC_LITERAL_REFERENCE_BC 1  /* mask b on level 0 only, like src/pmg.hpp:100-103 */
+#define PMGX_VC_DIAGNOSTICS 2           /* evaluate the reference's eager residual norms (quirk Q8) */
+int pmgx_vcycle_create(pmgx_ctx* ctx, int n_levels, pmgx_operator** ops, pmgx_cheb** smoothers,
+                       pmgx_interp** interps, const int8_t** bc_markers, pmgx_coarse* coarse,
+                       int flags, pmgx_vcycle** out);
+/* apply(x = b, y = u): one V-cycle on the top level; rnorm_h (may be NULL) receives
+ * ||b - A u|| after the cycle (the "rnorm after PMG" of :146-149). */
+int pmgx_vcycle_apply(pmgx_vcycle* vc, const double* b, double* u, double* rnorm_h);
+/* with PMGX_VC_DIAGNOSTICS: per-stage residual norms of the last apply, up to cap entries */
+int pmgx_vcycle_get_diagnostics(pmgx_vcycle* vc, double* out_h, int cap, int* n_h);
+int pmgx_vcycle_destroy(pmgx_vcycle* vc);
+
+/* -------------------------------------------------------- box mesh (host) -- */
+/* Harness-side stand-in for mesh::create_box + ghost_layer_mesh + compute_boundary_cells +
+ * tp dofmaps + exterior-facet BC markers + IndexMap/Scatterer lists (examples/pmg/main.cpp:
+ * 83-124,173-185,412-451; src/mesh.hpp:16-143).  Pure host code, no GPU needed.  The box
+ * [0,1]^3 with nx*ny*nz cells is split into px*py*pz blocks; `rank` selects the block.
+ * perturb > 0 displaces interior vertices by U(-perturb*h, perturb*h) (hash-seeded, identical
+ * on all ranks). */
+int pmgx_boxmesh_create(int nx, int ny, int nz, int px, int py, int pz, int rank,
+                        double perturb, uint64_t seed, pmgx_boxmesh** out);
+int pmgx_boxmesh_destroy(pmgx_boxmesh* m);
+/* sizes: out_h[0]=n_cells (owned+ghost) [1]=n_owned_cells [2]=n_points [3]=n_lcells [4]=n_bcells */
+int pmgx_boxmesh_sizes(pmgx_boxmesh* m, long long* out_h);
+int pmgx_boxmesh_geometry(pmgx_boxmesh* m, double* xgeom_h, int32_t* geom_dofmap_h);
+int pmgx_boxmesh_cell_lists(pmgx_boxmesh* m, int32_t* lcells_h, int32_t* bcells_h);
+/* per-degree space: out_h[0]=n_owned [1]=n_ghost [2]=n_send_nbr [3]=n_send_total
+ * [4]=n_recv_nbr [5]=n_recv_total [6]=n_global */
+int pmgx_boxmesh_space_sizes(pmgx_boxmesh* m, int degree, long long* out_h);
+/* dofmap_h[n_cells][(P+1)^3], bc_h[n_owned+n_ghost], l2g_h[n_owned+n_ghost] (canonical
+ * lexicographic global id), coords_h[n_owned+n_ghost][3]; any may be NULL. */
+int pmgx_boxmesh_space(pmgx_boxmesh* m, int degree, int32_t* dofmap_h, int8_t* bc_h,
+                       long long* l2g_h, double* coords_h);
+int pmgx_boxmesh_halo_lists(pmgx_boxmesh* m, int degree, int* send_ranks_h, int* send_offsets_h,
+                            int32_t* send_idx_h, int* recv_ranks_h, int* recv_offsets_h,
+                            int32_t* recv_idx_h);
+/* Mesh-size fit of the drivers (examples/pmg/main.cpp:412-435): cells per direction whose
+ * (n*order+1)^3 dof count is closest to ndofs_total. */
+int pmgx_boxmesh_fit(long long ndofs_total, int order, int* nxyz_h);
+
+/* GLL-collocated load vector b_i = sum_K f(x_i) w_i |detJ_K| followed by set_bc(b = g)
+ * (fem::assemble_vector + set_bc with the GLL rule, examples/pmg/main.cpp:289-295). f is
+ * evaluated by the caller: fvals[n_owned+n_ghost] device array of f at the dof coordinates.
+ * Result is complete on owned dofs (ghost cells contribute, like the operator). */
+int pmgx_laplacian_rhs(pmgx_operator* lap, const double* fvals, double g, double* b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMGX_H */

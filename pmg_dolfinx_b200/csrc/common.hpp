@@ -1,0 +1,167 @@
+// Shared internals of libpmgx: context, error handling, launch helpers.
+// Replaces src/util.hpp (err_check / device_synchronize) of the reference: errors are
+// returned through the C ABI instead of printf + exit(1) (src/util.hpp:21-29).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <memory>
+#include <algorithm>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/pmgx.h"
+
+namespace pmgx
+{
+void set_error(const char* fmt, ...);
+
+struct Error
+{
+  int code;
+};
+
+#define PMGX_CUDA(call)                                                                            \
+  do                                                                                               \
+  {                                                                                                \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+    {                                                                                              \
+      pmgx::set_error("%s:%d CUDA error: %s (%s)", __FILE__, __LINE__, cudaGetErrorString(_e),     \
+                      #call);                                                                      \
+      throw pmgx::Error{PMGX_ERR_CUDA};                                                            \
+    }                                                                                              \
+  } while (0)
+
+#define PMGX_NCCL(call)                                                                            \
+  do                                                                                               \
+  {                                                                                                \
+    ncclResult_t _e = (call);                                                                      \
+    if (_e != ncclSuccess)                                                                         \
+    {                                                                                              \
+      pmgx::set_error("%s:%d NCCL error: %s (%s)", __FILE__, __LINE__, ncclGetErrorString(_e),     \
+                      #call);                                                                      \
+      throw pmgx::Error{PMGX_ERR_NCCL};                                                            \
+    }                                                                                              \
+  } while (0)
+
+#define PMGX_REQUIRE(cond, ...)                                                                    \
+  do                                                                                               \
+  {                                                                                                \
+    if (!(cond))                                                                                   \
+    {                                                                                              \
+      pmgx::set_error(__VA_ARGS__);                                                                \
+      throw pmgx::Error{PMGX_ERR_ARG};                                                             \
+    }                                                                                              \
+  } while (0)
+
+// Wrap the body of every extern "C" entry point.
+#define PMGX_API_BEGIN try {
+#define PMGX_API_END                                                                               \
+  }                                                                                                \
+  catch (const pmgx::Error& e) { return e.code; }                                                  \
+  catch (const std::exception& e)                                                                  \
+  {                                                                                                \
+    pmgx::set_error("exception: %s", e.what());                                                    \
+    return PMGX_ERR_ARG;                                                                           \
+  }                                                                                                \
+  return PMGX_OK;
+
+template <typename T>
+struct DevBuf
+{
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n)
+  {
+    o.p = nullptr;
+    o.n = 0;
+  }
+  ~DevBuf() { release(); }
+  void alloc(size_t count)
+  {
+    release();
+    n = count;
+    if (count > 0)
+      PMGX_CUDA(cudaMalloc(&p, count * sizeof(T)));
+  }
+  void release()
+  {
+    if (p)
+      cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  void upload(const T* h, size_t count, cudaStream_t s)
+  {
+    alloc(count);
+    if (count > 0)
+    {
+      PMGX_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+      PMGX_CUDA(cudaStreamSynchronize(s));
+    }
+  }
+};
+} // namespace pmgx
+
+// Opaque context: one per GPU/rank.
+struct pmgx_ctx
+{
+  int device = 0;
+  int rank = 0;
+  int nranks = 1;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;      // compute stream
+  cudaStream_t comm_stream = nullptr; // halo pack / NCCL / unpack
+  ncclComm_t comm = nullptr;
+  // scratch for reductions: device partials + pinned host result
+  double* d_scalars = nullptr;        // [64] device scalars (dot results, alpha, beta, ...)
+  double* h_scalars = nullptr;        // pinned mirror
+  unsigned int* d_counter = nullptr;  // last-block-done counters
+  double* d_partials = nullptr;       // [max_blocks * 4]
+  int max_red_blocks = 0;
+  long long launches = 0;
+};
+
+namespace pmgx
+{
+inline void count_launch(pmgx_ctx* ctx, int n = 1) { ctx->launches += n; }
+inline void check_launch(const char* what)
+{
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+  {
+    set_error("kernel launch failed (%s): %s", what, cudaGetErrorString(e));
+    throw Error{PMGX_ERR_CUDA};
+  }
+}
+
+// Host GLL tables (gll.cpp)
+void gll_points_weights(int n, std::vector<double>& x, std::vector<double>& w);
+void gll_deriv_matrix(const std::vector<double>& x, std::vector<double>& D); // D[q*n+i]
+void gll_interp_matrix(int pc, int pf, std::vector<double>& M);              // M[f*(pc+1)+c]
+
+// vector kernels (vector_ops.cu) -- device-scalar flavoured internals used by the solvers
+namespace vec
+{
+void set(pmgx_ctx* c, double* x, long long n, double v);
+void copy(pmgx_ctx* c, double* a, const double* b, long long n);
+void axpy(pmgx_ctx* c, double* r, double alpha, const double* x, const double* y, long long n);
+void scale(pmgx_ctx* c, double* r, double alpha, long long n);
+void pointwise_mult(pmgx_ctx* c, double* w, const double* x, const double* y, long long n);
+void mask_bc(pmgx_ctx* c, double* b, const int8_t* bc, long long n);
+// local dot into device scalar slot (no host sync); allreduce over ranks when nranks > 1
+void dot_device(pmgx_ctx* c, const double* a, const double* b, long long n, int slot);
+double read_scalar(pmgx_ctx* c, int slot); // blocking D2H of one scalar
+double dot(pmgx_ctx* c, const double* a, const double* b, long long n);
+double norm_linf(pmgx_ctx* c, const double* a, long long n);
+} // namespace vec
+} // namespace pmgx

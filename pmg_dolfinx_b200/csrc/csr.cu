@@ -1,0 +1,156 @@
+// Assembled CSR operator for the coarse P1 level (north_star item 5).
+// Replaces spmv_impl (src/csr.hpp:20-36) and acc::MatrixOperator::operator()
+// (src/csr.hpp:220-273): a sub-warp of 8 lanes per row (P1 hex rows hold <= 27 entries)
+// with a shuffle reduction instead of one thread per row; the owned-column block runs while
+// the halo is in flight, the ghost-column block after it (same split at off_diag_offset).
+#include "common.hpp"
+#include "operator.hpp"
+#include "csr.hpp"
+
+namespace pmgx
+{
+namespace
+{
+constexpr int LPR = 8; // lanes per row
+constexpr int ST = 256;
+
+// y[i] (=|+=) sum_{j in [beg[i], end[i])} v[j] x[col[j]]
+template <bool ACCUM>
+__global__ void __launch_bounds__(ST)
+k_spmv(int n_rows, const double* __restrict__ vals, const int32_t* __restrict__ beg,
+       const int32_t* __restrict__ end, const int32_t* __restrict__ cols,
+       const double* __restrict__ x, double* __restrict__ y)
+{
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = gt / LPR, lane = gt % LPR;
+  double s = 0.0;
+  if (row < n_rows)
+  {
+    const int e = end[row];
+    for (int j = beg[row] + lane; j < e; j += LPR)
+      s = fma(vals[j], x[cols[j]], s);
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1)
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (row < n_rows && lane == 0)
+    y[row] = ACCUM ? y[row] + s : s;
+}
+
+__global__ void k_extract_diag_inv(int n_rows, const double* __restrict__ vals,
+                                   const int32_t* __restrict__ row_ptr,
+                                   const int32_t* __restrict__ cols, double* __restrict__ dinv)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows)
+    return;
+  double d = 0.0;
+  for (int j = row_ptr[i]; j < row_ptr[i + 1]; ++j)
+    if (cols[j] == i)
+      d = 1.0 / vals[j]; // src/csr.hpp:104-111
+  dinv[i] = d;
+}
+} // namespace
+
+void CsrOperator::apply(double* x, double* y)
+{
+  cudaSetDevice(ctx->device);
+  const int grid = (int)(((long long)n_owned * LPR + ST - 1) / ST);
+  // ghost entries of y are zeroed like y.set(0) (src/csr.hpp:225)
+  if (n_ghost > 0)
+    PMGX_CUDA(cudaMemsetAsync(y + n_owned, 0, (size_t)n_ghost * sizeof(double), ctx->stream));
+  if (halo)
+    halo_fwd_begin(halo, x);                                                       // :255
+  if (n_owned > 0)
+  {
+    k_spmv<false><<<grid, ST, 0, ctx->stream>>>(n_owned, values.p, row_ptr.p, off_diag.p, cols.p, x, y); // :256-260
+    check_launch("k_spmv");
+    count_launch(ctx);
+  }
+  if (halo)
+    halo_fwd_end(halo, x);                                                         // :262
+  if (n_owned > 0 && has_ghost_cols)
+  {
+    k_spmv<true><<<grid, ST, 0, ctx->stream>>>(n_owned, values.p, off_diag.p, row_ptr.p + 1, cols.p, x, y); // :264-268
+    check_launch("k_spmv");
+    count_launch(ctx);
+  }
+}
+
+void CsrOperator::finish_setup()
+{
+  diag_inv.alloc((size_t)n_owned);
+  if (n_owned > 0)
+  {
+    k_extract_diag_inv<<<(n_owned + 255) / 256, 256, 0, ctx->stream>>>(n_owned, values.p, row_ptr.p,
+                                                                       cols.p, diag_inv.p);
+    check_launch("k_extract_diag_inv");
+    count_launch(ctx);
+    PMGX_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+}
+} // namespace pmgx
+
+using pmgx::CsrOperator;
+
+extern "C"
+{
+int pmgx_csr_create(pmgx_ctx* ctx, int n_rows, int n_ghost, const int32_t* row_ptr_h,
+                    const int32_t* off_diag_offset_h, const int32_t* cols_h, const double* values_h,
+                    pmgx_halo* halo, pmgx_operator** out)
+{
+  PMGX_API_BEGIN
+  PMGX_REQUIRE(ctx && out && row_ptr_h, "csr_create: null argument");
+  PMGX_REQUIRE(n_rows >= 0 && n_ghost >= 0, "csr_create: bad sizes");
+  PMGX_CUDA(cudaSetDevice(ctx->device));
+  const long long nnz = row_ptr_h[n_rows];
+  PMGX_REQUIRE(row_ptr_h[0] == 0 && nnz >= 0, "csr_create: bad row_ptr");
+  bool ghost_cols = false;
+  for (int i = 0; i < n_rows; ++i)
+  {
+    PMGX_REQUIRE(row_ptr_h[i] <= off_diag_offset_h[i] && off_diag_offset_h[i] <= row_ptr_h[i + 1],
+                 "csr_create: off_diag_offset outside its row");
+    ghost_cols = ghost_cols || off_diag_offset_h[i] < row_ptr_h[i + 1];
+  }
+  for (long long j = 0; j < nnz; ++j)
+    PMGX_REQUIRE(cols_h[j] >= 0 && cols_h[j] < n_rows + n_ghost, "csr_create: column out of range");
+  std::unique_ptr<CsrOperator> A(new CsrOperator());
+  A->ctx = ctx;
+  A->kind = pmgx_operator::CSR;
+  A->n_owned = n_rows;
+  A->n_ghost = n_ghost;
+  A->halo = halo;
+  A->nnz = nnz;
+  A->has_ghost_cols = ghost_cols;
+  A->row_ptr.upload(row_ptr_h, (size_t)n_rows + 1, ctx->stream);
+  A->off_diag.upload(off_diag_offset_h, (size_t)n_rows, ctx->stream);
+  A->cols.upload(cols_h, (size_t)nnz, ctx->stream);
+  A->values.upload(values_h, (size_t)nnz, ctx->stream);
+  A->finish_setup();
+  *out = A.release();
+  PMGX_API_END
+}
+
+long long pmgx_csr_nnz(pmgx_operator* op)
+{
+  if (!op || op->kind != pmgx_operator::CSR)
+    return -1;
+  return static_cast<CsrOperator*>(op)->nnz;
+}
+
+int pmgx_csr_get(pmgx_operator* op, int32_t* row_ptr_h, int32_t* cols_h, double* values_h)
+{
+  PMGX_API_BEGIN
+  PMGX_REQUIRE(op && op->kind == pmgx_operator::CSR, "csr_get: not a CSR operator");
+  auto* A = static_cast<CsrOperator*>(op);
+  PMGX_CUDA(cudaSetDevice(A->ctx->device));
+  PMGX_CUDA(cudaStreamSynchronize(A->ctx->stream));
+  if (row_ptr_h)
+    PMGX_CUDA(cudaMemcpy(row_ptr_h, A->row_ptr.p, ((size_t)A->n_owned + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (cols_h && A->nnz > 0)
+    PMGX_CUDA(cudaMemcpy(cols_h, A->cols.p, (size_t)A->nnz * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (values_h && A->nnz > 0)
+    PMGX_CUDA(cudaMemcpy(values_h, A->values.p, (size_t)A->nnz * sizeof(double), cudaMemcpyDeviceToHost));
+  PMGX_API_END
+}
+}

@@ -1,0 +1,44 @@
+// Internal operator / halo types behind the opaque C handles.
+#pragma once
+#include "common.hpp"
+
+// Forward-scatter plan (role of dolfinx::common::Scatterer + the pack/unpack buffers of
+// acc::Vector, src/vector.hpp:83-95,186-238).
+struct pmgx_halo
+{
+  pmgx_ctx* ctx = nullptr;
+  int n_owned = 0, n_ghost = 0;
+  std::vector<int> send_ranks, send_offsets, recv_ranks, recv_offsets;
+  pmgx::DevBuf<int32_t> send_idx, recv_idx;
+  pmgx::DevBuf<double> send_buf, recv_buf;
+  cudaEvent_t ev_ready = nullptr; // compute stream -> comm stream (x is ready to pack)
+  cudaEvent_t ev_done = nullptr;  // comm stream -> compute stream (ghosts are in place)
+  bool in_flight = false;
+  int n_send() const { return send_offsets.empty() ? 0 : send_offsets.back(); }
+  int n_recv() const { return recv_offsets.empty() ? 0 : recv_offsets.back(); }
+};
+
+namespace pmgx
+{
+void halo_fwd_begin(pmgx_halo* h, double* x);
+void halo_fwd_end(pmgx_halo* h, double* x);
+} // namespace pmgx
+
+// Operator concept of the reference (operator()(in,out) + get_diag_inverse,
+// src/chebyshev.hpp:53-56, src/cg.hpp:154-159) as a small polymorphic base.
+struct pmgx_operator
+{
+  enum Kind
+  {
+    LAPLACIAN = 1,
+    CSR = 2
+  };
+  pmgx_ctx* ctx = nullptr;
+  Kind kind = LAPLACIAN;
+  int n_owned = 0, n_ghost = 0;
+  pmgx_halo* halo = nullptr;          // borrowed
+  pmgx::DevBuf<double> diag_inv;      // n_owned
+  virtual ~pmgx_operator() {}
+  // y = A x (zero fill + halo update of x included)
+  virtual void apply(double* x, double* y) = 0;
+};

@@ -1,0 +1,127 @@
+"""GPU parity: matrix-free Laplacian, geometry factors, diagonal.
+
+Tolerance (north_star): operator action relative 1e-12 in FP64, max- and 2-norm, against the
+oracle on the same mesh, degree and input; checked on the uniform cube and on the seeded
+perturbed mesh (which exposes G-indexing errors the uniform cube hides, quirk Q1).
+"""
+import numpy as np
+import pytest
+
+from oracle import mesh as om, operator as oo
+from helpers import OracleLevel, GpuLevel, rel
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.mark.parametrize("P", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("perturb", [0.0, 0.2])
+def test_apply_matches_oracle(ctx, P, perturb):
+    n = (3, 4, 5) if P <= 4 else (2, 3, 2)
+    ol = OracleLevel(om.create_box(*n, perturb=perturb), P)
+    gl = GpuLevel(ctx, ol)
+    rng = np.random.default_rng(42)
+    for x in (rng.uniform(-1, 1, ol.nd), np.ones(ol.nd)):
+        y, yo = gl.apply(x), ol.A(x)
+        e2, einf = rel(y, yo)
+        assert e2 < TOL and einf < TOL, (P, perturb, e2, einf)
+
+
+@pytest.mark.parametrize("P", [1, 3, 4, 6])
+def test_apply_cell_lists_and_ragged_batches(ctx, P):
+    """lcells/bcells in arbitrary order, sizes not a multiple of the cells-per-block batch."""
+    ol = OracleLevel(om.create_box(3, 3, 5, perturb=0.15), P)
+    rng = np.random.default_rng(7)
+    perm = rng.permutation(ol.mesh.ncells).astype(np.int32)
+    gl = GpuLevel(ctx, ol, lcells=perm[:17], bcells=perm[17:])
+    x = rng.uniform(-1, 1, ol.nd)
+    e2, einf = rel(gl.apply(x), ol.A(x))
+    assert e2 < TOL and einf < TOL
+
+
+def test_apply_subset_of_cells_and_empty_lists(ctx):
+    """Only the listed cells contribute (reference: entities list, laplacian.hpp:182); empty
+    lists give y = 0."""
+    P = 2
+    ol = OracleLevel(om.create_box(3, 3, 3), P)
+    cells = np.array([0, 5, 13, 26], dtype=np.int32)
+    gl = GpuLevel(ctx, ol, lcells=cells[:1], bcells=cells[1:])
+    x = np.random.default_rng(3).uniform(-1, 1, ol.nd)
+    yo = oo.apply_cells(P, ol.dm, ol.G, ol.kappa, ol.bc, x, np.zeros(ol.nd), cells)
+    e2, _ = rel(gl.apply(x), yo)
+    assert e2 < TOL
+    g0 = GpuLevel(ctx, ol, lcells=np.zeros(0, np.int32), bcells=np.zeros(0, np.int32))
+    assert np.abs(g0.apply(x)).max() == 0.0
+
+
+@pytest.mark.parametrize("P", [1, 2, 3, 4, 6])
+def test_geometry_factors_match_oracle(ctx, P):
+    for literal in (False, True):
+        ol = OracleLevel(om.create_box(2, 3, 2, perturb=0.2), P, literal_detj=literal)
+        gl = GpuLevel(ctx, ol, flags=1 if literal else 0)
+        G = gl.op.geometry_factors()
+        assert np.abs(G - ol.G).max() / np.abs(ol.G).max() < 1e-13
+
+
+def test_uniform_cube_G_is_diagonal(ctx):
+    """Known answer: uniform cube with h = 1/n gives G = diag(h w_q)."""
+    n, P = 4, 3
+    ol = OracleLevel(om.create_box(n, n, n), P)
+    G = GpuLevel(ctx, ol).op.geometry_factors()
+    w = oo.weights_3d(P)
+    assert np.abs(G[:, :, [1, 2, 4]]).max() < 1e-15 * np.abs(G).max()
+    for c in (0, 3, 5):
+        assert np.allclose(G[:, :, c], w[None, :] / n, rtol=1e-14, atol=0)
+
+
+@pytest.mark.parametrize("P", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_diag_inverse_matches_assembled_diagonal(ctx, P):
+    n = (3, 2, 3) if P <= 4 else (2, 2, 2)
+    ol = OracleLevel(om.create_box(*n, perturb=0.2), P)
+    gl = GpuLevel(ctx, ol)
+    v = gl.vec()
+    gl.op.get_diag_inverse(v)
+    d = 1.0 / v.data_copy()
+    do = ol.diag()
+    assert np.abs(d - do).max() / np.abs(do).max() < 1e-13
+    assert (d[ol.bc != 0] == 1.0).all()
+
+
+def test_known_answers_constant_and_linear(ctx):
+    """A * const = 0 and A * linear = 0 at rows whose cells touch no Dirichlet dof (affine mesh)."""
+    P, n = 3, 4
+    ol = OracleLevel(om.create_box(n, n, n), P)
+    gl = GpuLevel(ctx, ol)
+    X = om.dof_coords(ol.mesh, P)
+    touched = np.zeros(ol.nd, dtype=bool)
+    cell_has_bc = (ol.bc[ol.dm] != 0).any(axis=1)
+    touched[ol.dm[cell_has_bc].reshape(-1)] = True
+    scale = np.abs(ol.A(np.random.default_rng(0).uniform(-1, 1, ol.nd))).max()
+    for f in (np.ones(ol.nd), X[:, 0] + 2 * X[:, 1] - X[:, 2]):
+        y = gl.apply(f)
+        assert np.abs(y[~touched]).max() < 1e-13 * scale
+
+
+def test_symmetry(ctx):
+    ol = OracleLevel(om.create_box(3, 3, 3, perturb=0.2), 4)
+    gl = GpuLevel(ctx, ol)
+    rng = np.random.default_rng(5)
+    x, y = rng.uniform(-1, 1, ol.nd), rng.uniform(-1, 1, ol.nd)
+    x[ol.bc != 0] = 0
+    y[ol.bc != 0] = 0
+    a, b = np.dot(y, gl.apply(x)), np.dot(x, gl.apply(y))
+    assert abs(a - b) < 1e-12 * abs(a)
+
+
+def test_unsupported_degree_and_size_errors(ctx):
+    from pmg_dolfinx_b200 import api
+    ol = OracleLevel(om.create_box(2, 2, 2), 2)
+    gl = GpuLevel(ctx, ol)
+    with pytest.raises(api.PmgxError, match="Unsupported degree"):
+        api.MatFreeLaplacian(ctx, 9, gl.kappa, gl.dofmap, gl.xgeom, gl.gdm, gl.lcells, gl.bcells, gl.bc, ol.nd)
+    with pytest.raises(api.PmgxError):
+        api.MatFreeLaplacian(ctx, 2, gl.kappa, gl.dofmap, gl.xgeom, gl.gdm, np.array([99], np.int32), gl.bcells,
+                             gl.bc, ol.nd)
+    a, b = api.Vector(ctx, 5), api.Vector(ctx, 6)
+    with pytest.raises(api.PmgxError, match="Incompatible vector sizes"):
+        api.inner_product(a, b)
