@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- p-MG hot path benchmark (contract: one JSON line on rank 0).
+
+Workload (BASELINE.json configs[4], "examples/pmg"): Poisson on a unit-cube hex mesh, p-multigrid
+V-cycle P4 -> P2 -> P1, 4th-kind Chebyshev smoother with 2 iterations per level, lambda_max from
+a 20-iteration Jacobi-CG with b = 1 (examples/pmg/main.cpp:306-330), assembled-CSR Jacobi-PCG
+coarse solve behind the coarse-solver hook, ~100 M P4 dofs per GPU (weak scaling: the mesh-fit
+routine of examples/pmg/main.cpp:412-435 is run on ndofs * n_gpus).  One "step" = one V-cycle
+(MultigridPreconditioner::apply, src/pmg.hpp:56-155).  metric = fine-level Gdof/s per V-cycle;
+the per-apply throughput of the fine-level operator and its HBM roofline fraction are reported
+in "apply" / "roofline".
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--ndofs D] [--impl reference]
+  torchrun --nproc-per-node N bench.py --gpus N ...     (one rank per GPU, NCCL halo exchange)
+
+--impl reference: the reference's CPU path cannot be installed here (DOLFINx/PETSc absent), so
+the arm times the oracle's C/OpenMP restatement of the same V-cycle on the host cores, on a
+bounded sample of the workload (see "cpu_baseline.sample").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DEGREES = (1, 2, 4)
+NSMOOTH = 2
+COARSE_ITS, COARSE_RTOL = 60, 1e-4
+PGRID = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+METRIC = "fine-level Gdof/s per p-MG V-cycle (P4->P2->P1, Chebyshev(2), CSR coarse solve)"
+
+
+def b_apply(P, ncells, ndofs):
+    """Algorithmic bytes of one operator apply."""
+    return ncells * ((P + 1) ** 3 * 52 + 8) + ndofs * 17
+
+
+def measured_peak():
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(pk["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------ clocks --
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, dev):
+        self.dev, self.rows, self.proc = dev, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.dev)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------- CPU (oracle) arm --
+def cpu_vcycle_setup(n_cells_1d):
+    """Oracle V-cycle P4->P2->P1 on an n^3 sample, C/OpenMP kernels (oracle/c/pmg_oracle.c)."""
+    from oracle import mesh as om, operator as oo, solvers as osol, cport
+    m = om.create_box(n_cells_1d, n_cells_1d, n_cells_1d)
+    kap = np.full(m.ncells, 2.0)
+    levels, dms = [], {}
+    for P in DEGREES:
+        dm, bc, nd = om.dofmap(m, P), om.bc_marker(m, P), om.num_dofs(m, P)
+        dms[P] = (dm, nd)
+        G, _ = cport.geometry(m.verts, m.geom_dofmap, P)
+        A = cport.Apply(P, dm, G, kap, bc, nd)
+        dinv = 1.0 / oo.diagonal(P, dm, G, kap, bc, nd)
+        _, _, al, be, _, _ = osol.cg(A, dinv, np.zeros(nd), np.ones(nd), 20, 1e-6)
+        lmax = 1.1 * osol.lanczos_eigenvalues(al, be)[-1]
+        levels.append(osol.Level(A, dinv, bc.astype(float), lmax, NSMOOTH))
+        if P == DEGREES[0]:
+            A0 = oo.assemble_csr(P, dm, G, kap, bc, nd)
+            d0 = 1.0 / A0.diagonal()
+    pro, res = [], []
+    for a, b in zip(DEGREES[:-1], DEGREES[1:]):
+        mult = oo.multiplicity(dms[b][0], dms[b][1])
+        pro.append((lambda a, b: lambda xc: oo.prolong(a, b, dms[a][0], dms[b][0], xc, dms[b][1]))(a, b))
+        res.append((lambda a, b, mult: lambda xf: oo.restrict(a, b, dms[a][0], dms[b][0], xf, dms[a][1], mult))(a, b, mult))
+    coarse = lambda u0, b0: osol.cg(lambda v: cport.spmv(A0, v), d0, u0, b0, COARSE_ITS, COARSE_RTOL)[0]
+    Pt = DEGREES[-1]
+    b = oo.rhs_collocated(m, Pt, oo.f_sines(2, 3, 4, 2.0), om.bc_marker(m, Pt))
+    nd = dms[Pt][1]
+    step = lambda u: osol.vcycle(levels, pro, res, b, u, coarse_solve=coarse)
+    return step, nd, cport.num_threads(), levels[-1].A
+
+
+def cpu_baseline(steps=2, warmup=1, n=24):
+    step, nd, threads, A = cpu_vcycle_setup(n)
+    u = np.zeros(nd)
+    for _ in range(warmup):
+        u = step(u)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        u = step(u)
+    dt = (time.perf_counter() - t0) / steps
+    x = np.ones(nd)
+    y = np.empty(nd)
+    A(x, y)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        A(x, y)
+    dta = (time.perf_counter() - t0) / 5
+    return {"value": nd / dt / 1e9, "unit": "Gdof/s", "cores": threads, "kind": "port",
+            "sample": f"oracle C/OpenMP V-cycle P4->P2->P1 on a {n}^3-cell unit cube ({nd} P4 dofs), "
+                      f"{steps} timed V-cycles after {warmup} warm-up; same smoother/coarse settings",
+            "ms_per_step": dt * 1e3, "apply_gdofs": nd / dta / 1e9}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_baseline(steps=max(args.steps, 1), warmup=max(args.warmup, 1), n=args.cpu_cells)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "Gdof/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "examples/pmg P4->P2->P1 V-cycle (BASELINE configs[4]), CPU sample",
+                       "degrees": list(DEGREES), "smoother_its": NSMOOTH, "coarse": f"CSR Jacobi-PCG <= {COARSE_ITS} its",
+                       "note": "reference's DOLFINx/PETSc CPU path not installable here; oracle C/OpenMP port timed"},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": "Gdof/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------ GPU arm --
+def build_problem(ctx, api, torch, mesh, halos_on):
+    """Operators, smoothers, interpolators, coarse solver and V-cycle for one rank."""
+    lv = []
+    for P in DEGREES:
+        sp = mesh.space(P, want_coords=(P == DEGREES[-1]))
+        halo = api.Halo.from_space(ctx, sp) if halos_on else None
+        d = {"P": P, "sp": sp, "halo": halo, "dofmap": ctx.to_device(sp.dofmap), "bc": ctx.to_device(sp.bc)}
+        lv.append(d)
+    xgeom, gdm = ctx.to_device(mesh.xgeom), ctx.to_device(mesh.geom_dofmap)
+    kappa = torch.full((mesh.n_cells,), 2.0, dtype=torch.float64, device=ctx.device)
+    ops, smoothers, eigs = [], [], []
+    for d in lv:
+        sp = d["sp"]
+        op = api.MatFreeLaplacian(ctx, d["P"], kappa, d["dofmap"], xgeom, gdm, mesh.lcells, mesh.bcells, d["bc"],
+                                  sp.n_owned, sp.n_ghost, d["halo"])
+        cg = api.CGSolver(ctx, sp.n_owned, sp.n_ghost)
+        cg.set_max_iterations(20)
+        cg.set_tolerance(1e-6)
+        cg.store_coefficients(True)
+        x, y = api.Vector(ctx, sp.n_owned, sp.n_ghost), api.Vector(ctx, sp.n_owned, sp.n_ghost)
+        y.set(1.0)
+        cg.solve(op, x, y)
+        eig = cg.compute_eigenvalues()
+        s = api.Chebyshev(ctx, sp.n_owned, sp.n_ghost, (0.1 * eig[-1], 1.1 * eig[-1]))
+        s.set_max_iterations(NSMOOTH)
+        ops.append(op)
+        smoothers.append(s)
+        eigs.append(float(eig[-1]))
+        del cg, x, y
+    interps = []
+    for a, b in zip(lv[:-1], lv[1:]):
+        interps.append(api.Interpolator(ctx, a["P"], b["P"], a["dofmap"], b["dofmap"],
+                                        a["sp"].n_owned + a["sp"].n_ghost, b["sp"].n_owned + b["sp"].n_ghost,
+                                        mesh.lcells, mesh.bcells, a["halo"], b["halo"]))
+    A0 = ops[0].to_csr()
+    coarse = api.CoarseSolverType(ctx, A0, COARSE_ITS, COARSE_RTOL)
+    pmg = api.MultigridPreconditioner(ctx, [d["bc"] for d in lv])
+    pmg.set_solvers(smoothers)
+    pmg.set_operators(ops)
+    pmg.set_interpolators(interps)
+    pmg.set_coarse_solver(coarse)
+    top = lv[-1]
+    sp = top["sp"]
+    X = sp.coords
+    kx, ky, kz, kap = 2, 3, 4, 2.0
+    f = (kap * np.pi ** 2 * (kx * kx + ky * ky + kz * kz) * np.sin(kx * np.pi * X[:, 0]) * np.sin(ky * np.pi * X[:, 1])
+         * np.sin(kz * np.pi * X[:, 2]))
+    b = api.Vector(ctx, sp.n_owned, sp.n_ghost, top["halo"])
+    ops[-1].assemble_rhs(ctx.to_device(f), 0.0, b)
+    sp.coords = None
+    keep = (lv, xgeom, gdm, kappa, A0, coarse, interps, smoothers)
+    return pmg, ops, b, eigs, keep
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local)
+    from pmg_dolfinx_b200 import api
+    nccl_id = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        box = [api.Context.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        nccl_id = box[0]
+    ctx = api.Context(local, rank, world, nccl_id)
+
+    def barrier():
+        ctx.sync()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    Ptop = DEGREES[-1]
+    n = api.boxmesh_fit(args.ndofs * world, Ptop)
+    mesh = api.BoxMesh(n, PGRID[world], rank)
+    pmg, ops, b, eigs, keep = build_problem(ctx, api, torch, mesh, world > 1)
+    sp = keep[0][-1]["sp"]
+    n_owned = sp.n_owned
+    nd_global = sp.n_global
+    u = api.Vector(ctx, sp.n_owned, sp.n_ghost)
+    rn0 = api.norm(b)
+    # warm-up
+    for _ in range(args.warmup):
+        pmg.apply(b, u)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count()
+    api.check(api.lib.pmgx_ctx_profile(ctx.h, 1))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(ctx.stream)
+    for _ in range(args.steps):
+        pmg.apply(b, u)
+    e1.record(ctx.stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    import ctypes
+    kms, kl = ctypes.c_double(), ctypes.c_longlong()
+    api.check(api.lib.pmgx_ctx_profile_read(ctx.h, Ptop, ctypes.addressof(kms), ctypes.addressof(kl)))
+    api.check(api.lib.pmgx_ctx_profile(ctx.h, 0))
+    launches = ctx.launch_count() - l0
+    rn = pmg.apply(b, u, verbose=True)  # residual after warmup+steps+1 cycles (untimed)
+    t = torch.tensor([ms], dtype=torch.float64, device=ctx.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    ms_per_step = ms_max / args.steps
+
+    # fine-level operator apply alone (the kernel the roofline is quoted on), incl. zero fill
+    x, y = api.Vector(ctx, sp.n_owned, sp.n_ghost, keep[0][-1]["halo"]), api.Vector(ctx, sp.n_owned, sp.n_ghost)
+    x.set(1.0)
+    for _ in range(3):
+        ops[-1](x, y)
+    barrier()
+    reps = 20
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record(ctx.stream)
+    for _ in range(reps):
+        ops[-1](x, y)
+    a1.record(ctx.stream)
+    barrier()
+    ta = torch.tensor([a0.elapsed_time(a1) / reps], dtype=torch.float64, device=ctx.device)
+    if world > 1:
+        dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+    apply_ms = float(ta.item())
+
+    # end-to-end through the public API with HOST buffers: H2D of b, V-cycle, D2H of u
+    hb = torch.empty(n_owned, dtype=torch.float64).pin_memory()
+    hu = torch.empty(n_owned, dtype=torch.float64).pin_memory()
+    hb.copy_(b.data[:n_owned])
+    e2e_steps = max(1, min(args.steps, 3))
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record(ctx.stream)
+    for _ in range(e2e_steps):
+        b.data[:n_owned].copy_(hb, non_blocking=True)
+        pmg.apply(b, u)
+        hu.copy_(u.data[:n_owned], non_blocking=True)
+    s1.record(ctx.stream)
+    barrier()
+    te = torch.tensor([s0.elapsed_time(s1) / e2e_steps], dtype=torch.float64, device=ctx.device)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te.item())
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        n_own_cells = mesh.n_owned_cells
+        launches_per_apply = 2 if len(mesh.bcells) > 0 and len(mesh.lcells) > 0 else 1
+        n_applies = kl.value / launches_per_apply
+        B = b_apply(Ptop, n_own_cells, n_owned)
+        achieved = B * n_applies / (kms.value * 1e-3) / 1e9 if kms.value > 0 else None
+        cb = cpu_baseline(n=args.cpu_cells) if world == 1 and not args.no_cpu else None
+        line = {
+            "metric": METRIC, "value": nd_global / ms_per_step / 1e6, "unit": "Gdof/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "examples/pmg: P4->P2->P1 V-cycle, ~100M P4 dofs per GPU (BASELINE configs[4])",
+                       "mesh_cells": list(n), "partition": list(PGRID[world]), "dofs_global": nd_global,
+                       "dofs_per_level_rank0": [d["sp"].n_owned for d in keep[0]], "degrees": list(DEGREES),
+                       "smoother": f"Chebyshev-4 Jacobi, {NSMOOTH} its", "lambda_max": eigs,
+                       "coarse": f"CSR Jacobi-PCG <= {COARSE_ITS} its, rtol {COARSE_RTOL}",
+                       "l2": "working set >> 126 MB L2, no flush needed",
+                       "residual_reduction_after_cycles": [args.warmup + args.steps + 1, rn / rn0]},
+            "apply": {"degree": Ptop, "ms": apply_ms, "gdofs": nd_global / apply_ms / 1e6,
+                      "gbs_algorithmic": B / apply_ms / 1e6, "frac_of_hbm_peak": B / apply_ms / 1e6 / peak,
+                      "note": "operator()(x,y) incl. zero fill of y and halo; max over ranks"},
+            "roofline": {"bound": "hbm", "kernel": f"k_apply<{Ptop}>", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak if achieved else None, "traffic": None,
+                         "peak_source": peak_src, "launches_timed": kl.value,
+                         "algorithmic_bytes_per_apply": B, "avg_launch_ms": kms.value / max(kl.value, 1)},
+            "e2e": {"value": nd_global / e2e_ms / 1e6, "unit": "Gdof/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": n_owned * 8 * world, "d2h_bytes_per_step": n_owned * 8 * world},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        if cb is not None:
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"]["apply_gdofs"] = cb["apply_gdofs"]
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ndofs", type=float, default=1e8, help="P4 dofs per GPU (weak scaling)")
+    ap.add_argument("--cpu-cells", type=int, default=24, help="cells per direction of the CPU sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.ndofs = int(args.ndofs)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -79,6 +79,11 @@ int pmgx_ctx_rank(pmgx_ctx* ctx);
 int pmgx_ctx_nranks(pmgx_ctx* ctx);
 /* number of kernels launched by this library on ctx since creation (bench "gpu_launches") */
 long long pmgx_ctx_launch_count(pmgx_ctx* ctx);
+/* Per-kernel timing of the matrix-free apply kernel (bench roofline): while on, every launch of
+ * the apply kernel is bracketed by CUDA events on the compute stream; _read synchronises and
+ * returns the summed device time and the launch count for one degree, then clears them. */
+int pmgx_ctx_profile(pmgx_ctx* ctx, int on);
+int pmgx_ctx_profile_read(pmgx_ctx* ctx, int degree, double* ms_total_h, long long* launches_h);
 
 /* ------------------------------------------------------------------ halo -- */
 /* Owner->ghost forward scatter plan (replaces dolfinx::common::Scatterer held by

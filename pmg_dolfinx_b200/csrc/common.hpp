@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/pmgx.h"
@@ -129,6 +130,8 @@ struct pmgx_ctx
   double* d_partials = nullptr;       // [max_blocks * 4]
   int max_red_blocks = 0;
   long long launches = 0;
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[PMGX_MAX_DEGREE + 1];
 };
 
 namespace pmgx
@@ -158,6 +161,7 @@ void axpy(pmgx_ctx* c, double* r, double alpha, const double* x, const double* y
 void scale(pmgx_ctx* c, double* r, double alpha, long long n);
 void pointwise_mult(pmgx_ctx* c, double* w, const double* x, const double* y, long long n);
 void mask_bc(pmgx_ctx* c, double* b, const int8_t* bc, long long n);
+void allreduce_scalars(pmgx_ctx* c, int slot, int count, bool is_max);
 // local dot into device scalar slot (no host sync); allreduce over ranks when nranks > 1
 void dot_device(pmgx_ctx* c, const double* a, const double* b, long long n, int slot);
 double read_scalar(pmgx_ctx* c, int slot); // blocking D2H of one scalar

@@ -88,6 +88,37 @@ int pmgx_ctx_sync(pmgx_ctx* c)
   PMGX_API_END
 }
 
+int pmgx_ctx_profile(pmgx_ctx* c, int on)
+{
+  PMGX_API_BEGIN
+  PMGX_REQUIRE(c, "ctx_profile: null ctx");
+  c->profiling = on != 0;
+  PMGX_API_END
+}
+
+int pmgx_ctx_profile_read(pmgx_ctx* c, int degree, double* ms_total_h, long long* launches_h)
+{
+  PMGX_API_BEGIN
+  PMGX_REQUIRE(c && degree >= 1 && degree <= PMGX_MAX_DEGREE, "ctx_profile_read: bad arguments");
+  PMGX_CUDA(cudaSetDevice(c->device));
+  PMGX_CUDA(cudaStreamSynchronize(c->stream));
+  double total = 0.0;
+  for (auto& pr : c->prof[degree])
+  {
+    float ms = 0.f;
+    PMGX_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+    total += ms;
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  if (ms_total_h)
+    *ms_total_h = total;
+  if (launches_h)
+    *launches_h = (long long)c->prof[degree].size();
+  c->prof[degree].clear();
+  PMGX_API_END
+}
+
 void* pmgx_ctx_stream(pmgx_ctx* c) { return c ? (void*)c->stream : nullptr; }
 int pmgx_ctx_rank(pmgx_ctx* c) { return c ? c->rank : -1; }
 int pmgx_ctx_nranks(pmgx_ctx* c) { return c ? c->nranks : -1; }

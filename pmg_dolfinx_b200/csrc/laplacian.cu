@@ -467,9 +467,21 @@ void launch_apply(pmgx_ctx* c, const double* x, double* y, const double* G, cons
     configured[c->device] = true;
   }
   const int grid = (count + C::cpb - 1) / C::cpb;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (c->profiling)
+  {
+    PMGX_CUDA(cudaEventCreate(&e0));
+    PMGX_CUDA(cudaEventCreate(&e1));
+    PMGX_CUDA(cudaEventRecord(e0, c->stream));
+  }
   k_apply<P><<<grid, C::tpb, smem, c->stream>>>(x, y, G, enc, perm, kappa, first, count);
   check_launch("k_apply");
   count_launch(c);
+  if (c->profiling)
+  {
+    PMGX_CUDA(cudaEventRecord(e1, c->stream));
+    c->prof[P].emplace_back(e0, e1);
+  }
 }
 
 void upload_tables(pmgx_ctx* c)

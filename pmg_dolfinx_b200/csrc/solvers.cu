@@ -14,10 +14,6 @@
 
 namespace pmgx
 {
-namespace vec
-{
-void allreduce_scalars(pmgx_ctx* c, int slot, int count, bool is_max);
-}
 namespace
 {
 constexpr int FT = RED_THREADS;
