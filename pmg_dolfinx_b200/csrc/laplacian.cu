@@ -25,6 +25,7 @@
 #include <thrust/scan.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace pmgx
@@ -32,6 +33,7 @@ namespace pmgx
 namespace
 {
 constexpr int MAXN = PMGX_MAX_DEGREE + 1;
+constexpr int SLAB_MAX_DEGREE = 4; // slab kernel (registers: 2 (P+1)^2 doubles) up to here, column kernel above
 
 // 1-D tables for every degree; index [P][...]
 __constant__ double c_D[PMGX_MAX_DEGREE + 1][MAXN * MAXN]; // D[q*n+i] = l_i'(x_q)
@@ -46,10 +48,46 @@ __device__ __forceinline__ double ldg_stream(const double* p)
 }
 __device__ __forceinline__ int ldg_stream_i32(const int* p) { return __ldcs(p); }
 
+
+// How the operator-private arrays (BC-encoded dofmap, geometry factors) are laid out.  The
+// reference keeps G private (src/laplacian.hpp:512), so the layout is free: it follows the
+// thread mapping of the apply kernel so that every warp load is one aligned, contiguous run.
+//   COLUMN: enc[p][n3], G[p][6][n3]                         (thread = (iy,iz) column, P >= 5)
+//   SLAB  : enc[batch][n2][S], G[batch][n2][6][S]           (thread = iz slab,        P <= 4)
+//           batch = CPB consecutive cells of the launch list, slot = cell_in_batch*n + iz,
+//           S = 128 slots (padded); lcells and bcells batches are padded separately.
+struct Lay
+{
+  int mode; // 0 COLUMN, 1 SLAB
+  int n, n2, n3;
+  int cpb, S;
+  int n_l, nb_l;
+  long long n_batches;
+  __host__ __device__ long long enc_size() const { return mode == 0 ? 0 : n_batches * n2 * S; }
+  __host__ __device__ long long enc_index(long long p, int a) const
+  {
+    if (mode == 0)
+      return p * n3 + a;
+    const long long pl = p < n_l ? p : p - n_l;
+    const long long batch = (p < n_l ? 0 : nb_l) + pl / cpb;
+    const int slot = (int)(pl % cpb) * n + a % n;
+    return (batch * n2 + a / n) * S + slot;
+  }
+  __host__ __device__ long long g_index(long long p, int comp, int q) const
+  {
+    if (mode == 0)
+      return (p * 6 + comp) * n3 + q;
+    const long long pl = p < n_l ? p : p - n_l;
+    const long long batch = (p < n_l ? 0 : nb_l) + pl / cpb;
+    const int slot = (int)(pl % cpb) * n + q % n;
+    return ((batch * n2 + q / n) * 6 + comp) * S + slot;
+  }
+};
+
 // ------------------------------------------------------------------ set-up kernels --
 __global__ void k_encode_dofmap(const int32_t* __restrict__ dofmap, const int32_t* __restrict__ perm,
                                 const int8_t* __restrict__ bc, int32_t* __restrict__ enc, int n3,
-                                long long total)
+                                long long total, Lay lay)
 {
   const long long nth = (long long)gridDim.x * blockDim.x;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += nth)
@@ -57,7 +95,7 @@ __global__ void k_encode_dofmap(const int32_t* __restrict__ dofmap, const int32_
     const long long p = t / n3;
     const int a = (int)(t - p * n3);
     const int32_t d = dofmap[(long long)perm[p] * n3 + a];
-    enc[t] = bc[d] ? ~d : d;
+    enc[lay.enc_index(p, a)] = bc[d] ? ~d : d;
   }
 }
 
@@ -67,7 +105,7 @@ template <bool WRITE_G>
 __global__ void k_geometry(int P, const double* __restrict__ xgeom,
                            const int32_t* __restrict__ geom_dofmap,
                            const int32_t* __restrict__ perm, double* __restrict__ G,
-                           double* __restrict__ detj_w, int n_list, bool literal_detj)
+                           double* __restrict__ detj_w, int n_list, bool literal_detj, Lay lay)
 {
   const int n = P + 1, n2 = n * n, n3 = n2 * n;
   const long long total = (long long)n_list * n3;
@@ -114,13 +152,12 @@ __global__ void k_geometry(int P, const double* __restrict__ xgeom,
     if (WRITE_G)
     {
       const double s = w / detJ;
-      double* g = G + p * 6 * n3 + q;
-      g[0 * n3] = (K[0][0] * K[0][0] + K[0][1] * K[0][1] + K[0][2] * K[0][2]) * s;
-      g[1 * n3] = (K[1][0] * K[0][0] + K[1][1] * K[0][1] + K[1][2] * K[0][2]) * s;
-      g[2 * n3] = (K[2][0] * K[0][0] + K[2][1] * K[0][1] + K[2][2] * K[0][2]) * s;
-      g[3 * n3] = (K[1][0] * K[1][0] + K[1][1] * K[1][1] + K[1][2] * K[1][2]) * s;
-      g[4 * n3] = (K[2][0] * K[1][0] + K[2][1] * K[1][1] + K[2][2] * K[1][2]) * s;
-      g[5 * n3] = (K[2][0] * K[2][0] + K[2][1] * K[2][1] + K[2][2] * K[2][2]) * s;
+      G[lay.g_index(p, 0, q)] = (K[0][0] * K[0][0] + K[0][1] * K[0][1] + K[0][2] * K[0][2]) * s;
+      G[lay.g_index(p, 1, q)] = (K[1][0] * K[0][0] + K[1][1] * K[0][1] + K[1][2] * K[0][2]) * s;
+      G[lay.g_index(p, 2, q)] = (K[2][0] * K[0][0] + K[2][1] * K[0][1] + K[2][2] * K[0][2]) * s;
+      G[lay.g_index(p, 3, q)] = (K[1][0] * K[1][0] + K[1][1] * K[1][1] + K[1][2] * K[1][2]) * s;
+      G[lay.g_index(p, 4, q)] = (K[2][0] * K[1][0] + K[2][1] * K[1][1] + K[2][2] * K[1][2]) * s;
+      G[lay.g_index(p, 5, q)] = (K[2][0] * K[2][0] + K[2][1] * K[2][1] + K[2][2] * K[2][2]) * s;
     }
     else
       detj_w[t] = w * fabs(detJ);
@@ -130,7 +167,7 @@ __global__ void k_geometry(int P, const double* __restrict__ xgeom,
 // diag(A) contributions, thread per (cell position, local dof); see DESIGN.md "diagonal".
 __global__ void k_diag(int P, const double* __restrict__ G, const int32_t* __restrict__ enc,
                        const int32_t* __restrict__ perm, const double* __restrict__ kappa,
-                       double* __restrict__ diag, int n_list)
+                       double* __restrict__ diag, int n_list, Lay lay)
 {
   const int n = P + 1, n2 = n * n, n3 = n2 * n;
   const long long total = (long long)n_list * n3;
@@ -139,22 +176,22 @@ __global__ void k_diag(int P, const double* __restrict__ G, const int32_t* __res
   {
     const long long p = t / n3;
     const int a = (int)(t - p * n3);
-    const int32_t d = enc[t];
+    const int32_t d = enc[lay.enc_index(p, a)];
     if (d < 0)
       continue;
     const int i = a / n2, j = (a / n) % n, k = a % n;
-    const double* g = G + p * 6 * n3;
     const double* D = c_D[P];
     double s = 0.0;
     for (int q = 0; q < n; ++q)
     {
       const double dx = D[q * n + i], dy = D[q * n + j], dz = D[q * n + k];
-      s += dx * dx * g[0 * n3 + q * n2 + j * n + k];
-      s += dy * dy * g[3 * n3 + i * n2 + q * n + k];
-      s += dz * dz * g[5 * n3 + i * n2 + j * n + q];
+      s += dx * dx * G[lay.g_index(p, 0, q * n2 + j * n + k)];
+      s += dy * dy * G[lay.g_index(p, 3, i * n2 + q * n + k)];
+      s += dz * dz * G[lay.g_index(p, 5, i * n2 + j * n + q)];
     }
     const double dii = D[i * n + i], djj = D[j * n + j], dkk = D[k * n + k];
-    s += 2.0 * (g[1 * n3 + a] * dii * djj + g[2 * n3 + a] * dii * dkk + g[4 * n3 + a] * djj * dkk);
+    s += 2.0 * (G[lay.g_index(p, 1, a)] * dii * djj + G[lay.g_index(p, 2, a)] * dii * dkk
+                + G[lay.g_index(p, 4, a)] * djj * dkk);
     atomicAdd(&diag[d], kappa[perm[p]] * s);
   }
 }
@@ -168,7 +205,7 @@ __global__ void k_invert_diag(const double* __restrict__ diag, const int8_t* __r
 }
 
 __global__ void k_G_to_reference_layout(const double* __restrict__ G, double* __restrict__ out,
-                                        int n3, long long total)
+                                        int n3, long long total, Lay lay)
 {
   const long long nth = (long long)gridDim.x * blockDim.x;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += nth)
@@ -176,17 +213,18 @@ __global__ void k_G_to_reference_layout(const double* __restrict__ G, double* __
     const long long p = t / (6 * n3);
     const int r = (int)(t - p * 6 * n3);
     const int q = r / 6, c = r % 6;
-    out[t] = G[p * 6 * n3 + (long long)c * n3 + q];
+    out[t] = G[lay.g_index(p, c, q)];
   }
 }
 
 __global__ void k_rhs(const double* __restrict__ detj_w, const int32_t* __restrict__ enc,
-                      const double* __restrict__ fvals, double* __restrict__ b, long long total)
+                      const double* __restrict__ fvals, double* __restrict__ b, long long total,
+                      int n3, Lay lay)
 {
   const long long nth = (long long)gridDim.x * blockDim.x;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += nth)
   {
-    const int32_t d = enc[t];
+    const int32_t d = enc[lay.enc_index(t / n3, (int)(t % n3))];
     if (d >= 0)
       atomicAdd(&b[d], fvals[d] * detj_w[t]);
   }
@@ -203,7 +241,7 @@ __global__ void k_set_bc_value(double* __restrict__ b, const int8_t* __restrict_
 // Entry (i,j) of the element matrix kappa * B^T G B with the collocated gradient table
 // (phi = identity at the GLL points, src/laplacian.hpp:200-202): only index pairs that
 // agree in at least one direction couple.
-__device__ double element_entry(int P, const double* __restrict__ g, int i, int j)
+__device__ double element_entry(int P, const double* __restrict__ G, const Lay& lay, long long p, int i, int j)
 {
   const int n = P + 1, n2 = n * n, n3 = n2 * n;
   const double* D = c_D[P];
@@ -212,22 +250,22 @@ __device__ double element_entry(int P, const double* __restrict__ g, int i, int 
   double s = 0.0;
   if (iy == jy && iz == jz)
     for (int q = 0; q < n; ++q)
-      s += D[q * n + ix] * D[q * n + jx] * g[0 * n3 + q * n2 + iy * n + iz];
+      s += D[q * n + ix] * D[q * n + jx] * G[lay.g_index(p, 0, q * n2 + iy * n + iz)];
   if (ix == jx && iz == jz)
     for (int q = 0; q < n; ++q)
-      s += D[q * n + iy] * D[q * n + jy] * g[3 * n3 + ix * n2 + q * n + iz];
+      s += D[q * n + iy] * D[q * n + jy] * G[lay.g_index(p, 3, ix * n2 + q * n + iz)];
   if (ix == jx && iy == jy)
     for (int q = 0; q < n; ++q)
-      s += D[q * n + iz] * D[q * n + jz] * g[5 * n3 + ix * n2 + iy * n + q];
+      s += D[q * n + iz] * D[q * n + jz] * G[lay.g_index(p, 5, ix * n2 + iy * n + q)];
   if (iz == jz)
-    s += D[jx * n + ix] * D[iy * n + jy] * g[1 * n3 + jx * n2 + iy * n + iz]
-         + D[jy * n + iy] * D[ix * n + jx] * g[1 * n3 + ix * n2 + jy * n + iz];
+    s += D[jx * n + ix] * D[iy * n + jy] * G[lay.g_index(p, 1, jx * n2 + iy * n + iz)]
+         + D[jy * n + iy] * D[ix * n + jx] * G[lay.g_index(p, 1, ix * n2 + jy * n + iz)];
   if (iy == jy)
-    s += D[jx * n + ix] * D[iz * n + jz] * g[2 * n3 + jx * n2 + iy * n + iz]
-         + D[jz * n + iz] * D[ix * n + jx] * g[2 * n3 + ix * n2 + iy * n + jz];
+    s += D[jx * n + ix] * D[iz * n + jz] * G[lay.g_index(p, 2, jx * n2 + iy * n + iz)]
+         + D[jz * n + iz] * D[ix * n + jx] * G[lay.g_index(p, 2, ix * n2 + iy * n + jz)];
   if (ix == jx)
-    s += D[jy * n + iy] * D[iz * n + jz] * g[4 * n3 + ix * n2 + jy * n + iz]
-         + D[jz * n + iz] * D[iy * n + jy] * g[4 * n3 + ix * n2 + iy * n + jz];
+    s += D[jy * n + iy] * D[iz * n + jz] * G[lay.g_index(p, 4, ix * n2 + jy * n + iz)]
+         + D[jz * n + iz] * D[iy * n + jy] * G[lay.g_index(p, 4, ix * n2 + iy * n + jz)];
   return s;
 }
 
@@ -236,7 +274,7 @@ __device__ double element_entry(int P, const double* __restrict__ g, int i, int 
 __global__ void k_element_triplets(int P, const double* __restrict__ G, const int32_t* __restrict__ enc,
                                    const int32_t* __restrict__ perm, const double* __restrict__ kappa,
                                    long long n_list, int n_owned, long long ntot,
-                                   unsigned long long* __restrict__ keys, double* __restrict__ vals)
+                                   unsigned long long* __restrict__ keys, double* __restrict__ vals, Lay lay)
 {
   const int n = P + 1, n3 = n * n * n;
   const long long per_cell = (long long)n3 * n3;
@@ -247,7 +285,7 @@ __global__ void k_element_triplets(int P, const double* __restrict__ G, const in
     const long long p = t / per_cell;
     const int r = (int)(t - p * per_cell);
     const int i = r / n3, j = r - i * n3;
-    const int32_t di = enc[p * n3 + i], dj = enc[p * n3 + j];
+    const int32_t di = enc[lay.enc_index(p, i)], dj = enc[lay.enc_index(p, j)];
     if (di < 0 || dj < 0 || di >= n_owned)
     {
       keys[t] = ~0ull;
@@ -255,7 +293,7 @@ __global__ void k_element_triplets(int P, const double* __restrict__ G, const in
       continue;
     }
     keys[t] = (unsigned long long)di * (unsigned long long)ntot + (unsigned long long)dj;
-    vals[t] = kappa[perm[p]] * element_entry(P, G + p * 6 * n3, i, j);
+    vals[t] = kappa[perm[p]] * element_entry(P, G, lay, p, i, j);
   }
 }
 
@@ -484,6 +522,538 @@ void launch_apply(pmgx_ctx* c, const double* x, double* y, const double* G, cons
   }
 }
 
+// ------------------------------------------------------------- the slab apply kernel --
+// Thread = one z-index k of one cell; it keeps the whole (ix,iy) slab of the element in
+// registers, so the x and y contractions are pure register FMAs with compile-time D entries
+// and only the z contraction exchanges data through shared memory (rows of n values that all
+// n threads of a cell read as a broadcast).  This moves ~1/3 of the bytes of the column
+// kernel through the LSU/shared-memory pipe, which ncu showed to be the limiter there
+// (l1tex data-pipe 80 % busy at 61 % DRAM, profiles/r1_apply_p4_column.txt).
+template <int P>
+struct SlabCfg
+{
+  static constexpr int n = P + 1;
+  static constexpr int n2 = n * n;
+  static constexpr int tpb = 128;
+  static constexpr int cpb = tpb / n;      // cells per block
+  static constexpr int S = tpb;            // slots per (batch, ix, iy) row of G / enc
+  static constexpr int kp = n + (n & 1);   // padded z-row (16-byte rows for double2 loads)
+  static constexpr int su_doubles = cpb * n2 * kp;
+  static constexpr int sf_doubles = 2 * cpb * n * kp;
+  static constexpr size_t smem = (size_t)(su_doubles + sf_doubles) * sizeof(double);
+};
+
+template <int P, int MINB>
+__global__ void __launch_bounds__(SlabCfg<P>::tpb, MINB)
+k_apply_slab(const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ G,
+             const int32_t* __restrict__ enc, const int32_t* __restrict__ perm,
+             const double* __restrict__ kappa, long long batch0, int cell0, int count)
+{
+  using C = SlabCfg<P>;
+  constexpr int n = C::n, n2 = C::n2, CPB = C::cpb, S = C::S, KP = C::kp;
+  extern __shared__ __align__(16) double smem[];
+  double* su = smem;                  // [CPB][n2][KP]
+  double* sf = smem + C::su_doubles;  // [2][CPB][n][KP]
+
+  const int tid = threadIdx.x;
+  const int cl = tid / n;
+  const int k = tid - cl * n;
+  const int pl = blockIdx.x * CPB + cl;
+  const bool in_block = cl < CPB;
+  const bool active = in_block && pl < count;
+  const long long gb = batch0 + blockIdx.x;
+  const int32_t* e = enc + gb * (n2 * S) + tid;
+  const double* g = G + gb * ((long long)n2 * 6 * S) + tid;
+  const int cls = in_block ? cl : 0;
+
+  int d[n2];
+  double u[n2];
+  double kap = 0.0;
+  if (active)
+  {
+#pragma unroll
+    for (int a = 0; a < n2; ++a)
+      d[a] = ldg_stream_i32(e + a * S);
+    kap = kappa[perm[cell0 + pl]];
+#pragma unroll
+    for (int a = 0; a < n2; ++a)
+    {
+      const int idx = d[a] < 0 ? ~d[a] : d[a];
+      const double xv = x[idx];
+      if (d[a] < 0)
+        y[idx] = xv; // Dirichlet row: y = x (src/laplacian.hpp:273-274)
+      u[a] = d[a] < 0 ? 0.0 : xv;
+    }
+  }
+  else
+  {
+#pragma unroll
+    for (int a = 0; a < n2; ++a)
+      d[a] = -1, u[a] = 0.0;
+  }
+  if (in_block)
+  {
+#pragma unroll
+    for (int a = 0; a < n2; ++a)
+      su[(cl * n2 + a) * KP + k] = u[a];
+  }
+  double Dk[n], DTk[n];
+#pragma unroll
+  for (int l = 0; l < n; ++l)
+  {
+    Dk[l] = c_D[P][k * n + l];
+    DTk[l] = c_D[P][l * n + k];
+  }
+  double acc[n2];
+#pragma unroll
+  for (int a = 0; a < n2; ++a)
+    acc[a] = 0.0;
+  __syncthreads();
+
+#pragma unroll
+  for (int i = 0; i < n; ++i)
+  {
+    double gg[n][6];
+    if (active)
+    {
+#pragma unroll
+      for (int j = 0; j < n; ++j)
+#pragma unroll
+        for (int c = 0; c < 6; ++c)
+          gg[j][c] = ldg_stream(g + ((i * n + j) * 6 + c) * S);
+    }
+    else
+    {
+#pragma unroll
+      for (int j = 0; j < n; ++j)
+#pragma unroll
+        for (int c = 0; c < 6; ++c)
+          gg[j][c] = 0.0;
+    }
+    double fz[n];
+#pragma unroll
+    for (int j = 0; j < n; ++j)
+    {
+      double gx = 0.0, gy = 0.0, gz = 0.0;
+      const double2* row = reinterpret_cast<const double2*>(su + (cls * n2 + i * n + j) * KP);
+#pragma unroll
+      for (int l2 = 0; l2 < KP / 2; ++l2)
+      {
+        const double2 r = row[l2];
+        gz = fma(Dk[2 * l2], r.x, gz);
+        if (2 * l2 + 1 < n)
+          gz = fma(Dk[2 * l2 + 1], r.y, gz);
+      }
+#pragma unroll
+      for (int l = 0; l < n; ++l)
+      {
+        gx = fma(c_D[P][i * n + l], u[l * n + j], gx);
+        gy = fma(c_D[P][j * n + l], u[i * n + l], gy);
+      }
+      const double fx = kap * (gg[j][0] * gx + gg[j][1] * gy + gg[j][2] * gz);
+      const double fy = kap * (gg[j][1] * gx + gg[j][3] * gy + gg[j][4] * gz);
+      fz[j] = kap * (gg[j][2] * gx + gg[j][4] * gy + gg[j][5] * gz);
+#pragma unroll
+      for (int l = 0; l < n; ++l)
+      {
+        acc[l * n + j] = fma(c_D[P][i * n + l], fx, acc[l * n + j]);
+        acc[i * n + l] = fma(c_D[P][j * n + l], fy, acc[i * n + l]);
+      }
+    }
+    double* sfz = sf + (((i & 1) * CPB + cls) * n) * KP;
+    if (in_block)
+    {
+#pragma unroll
+      for (int j = 0; j < n; ++j)
+        sfz[j * KP + k] = fz[j];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < n; ++j)
+    {
+      const double2* row = reinterpret_cast<const double2*>(sfz + j * KP);
+      double t = 0.0;
+#pragma unroll
+      for (int q2 = 0; q2 < KP / 2; ++q2)
+      {
+        const double2 r = row[q2];
+        t = fma(DTk[2 * q2], r.x, t);
+        if (2 * q2 + 1 < n)
+          t = fma(DTk[2 * q2 + 1], r.y, t);
+      }
+      acc[i * n + j] += t;
+    }
+  }
+  if (active)
+  {
+#pragma unroll
+    for (int a = 0; a < n2; ++a)
+      if (d[a] >= 0)
+        atomicAdd(&y[d[a]], acc[a]);
+  }
+}
+
+template <int P>
+constexpr int slab_minb()
+{
+  return P <= 2 ? 4 : (P == 3 ? 3 : 2);
+}
+
+template <int P>
+void launch_apply_slab(pmgx_ctx* c, const double* x, double* y, const double* G, const int32_t* enc,
+                       const int32_t* perm, const double* kappa, long long batch0, int cell0, int count)
+{
+  if (count <= 0)
+    return;
+  using C = SlabCfg<P>;
+  constexpr int MINB = slab_minb<P>();
+  static bool configured[64] = {false};
+  if (!configured[c->device])
+  {
+    PMGX_CUDA(cudaFuncSetAttribute(k_apply_slab<P, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)C::smem));
+    configured[c->device] = true;
+  }
+  const int grid = (count + C::cpb - 1) / C::cpb;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (c->profiling)
+  {
+    PMGX_CUDA(cudaEventCreate(&e0));
+    PMGX_CUDA(cudaEventCreate(&e1));
+    PMGX_CUDA(cudaEventRecord(e0, c->stream));
+  }
+  k_apply_slab<P, MINB><<<grid, C::tpb, C::smem, c->stream>>>(x, y, G, enc, perm, kappa, batch0, cell0, count);
+  check_launch("k_apply_slab");
+  count_launch(c);
+  if (c->profiling)
+  {
+    PMGX_CUDA(cudaEventRecord(e1, c->stream));
+    c->prof[P].emplace_back(e0, e1);
+  }
+}
+
+// --------------------------------------------- the TMA-pipelined slab apply kernel --
+// Same thread mapping and arithmetic as k_apply_slab, but the one-shot streams (geometry
+// factors, encoded dofmap) no longer pass through registers with the latency exposed to a
+// handful of resident warps: a persistent CTA walks over its batches and an elected thread
+// keeps a ring of R geometry planes (and the next batch's dofmap) in flight with
+// cp.async.bulk (TMA) into shared memory, completion tracked by mbarriers.  Memory-level
+// parallelism is then set by the ring depth, not by occupancy or register count.
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+  asm volatile("{\n"
+               ".reg .pred p;\n"
+               "WAIT_LOOP:\n"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+               "@p bra WAIT_DONE;\n"
+               "bra WAIT_LOOP;\n"
+               "WAIT_DONE:\n"
+               "}\n" ::"r"(smem_u32(bar)),
+               "r"(parity)
+               : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first()
+{
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+               "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+               : "memory");
+}
+
+template <int P, int R>
+struct TmaCfg
+{
+  static constexpr int n = P + 1;
+  static constexpr int n2 = n * n;
+  static constexpr int tpb = 128;
+  static constexpr int S = tpb;
+  static constexpr int cpb = tpb / n;
+  static constexpr int kp = n + (n & 1);
+  // per-cell stride of a z-row plane buffer: an odd number of 16-byte chunks, so the cells of
+  // a warp start in different bank groups (profiles/r1_apply_p3_slab.txt: 75 % of the shared
+  // wavefronts were conflict replays with the unpadded stride)
+  static constexpr int cs = ((n * kp / 2) & 1) ? n * kp : n * kp + 2;
+  static constexpr int plane_doubles = n * 6 * S;
+  static constexpr uint32_t plane_bytes = plane_doubles * sizeof(double);
+  static constexpr uint32_t enc_bytes = n2 * S * sizeof(int32_t);
+  static constexpr int buf_doubles = 2 * cpb * cs; // double-buffered plane rows (su and sf each)
+  static constexpr size_t off_enc = (size_t)R * plane_bytes;
+  static constexpr size_t off_su = off_enc + enc_bytes;
+  static constexpr size_t off_sf = off_su + (size_t)buf_doubles * sizeof(double);
+  static constexpr size_t off_bar = off_sf + (size_t)buf_doubles * sizeof(double);
+  static constexpr size_t smem = off_bar + (R + 1) * sizeof(uint64_t);
+};
+
+template <int P, int R, int MINB>
+__global__ void __launch_bounds__(TmaCfg<P, R>::tpb, MINB)
+k_apply_tma(const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ G,
+            const int32_t* __restrict__ enc, const int32_t* __restrict__ perm,
+            const double* __restrict__ kappa, long long batch0, int cell0, int count, int nbatch)
+{
+  using C = TmaCfg<P, R>;
+  constexpr int n = C::n, n2 = C::n2, CPB = C::cpb, S = C::S, KP = C::kp, CS = C::cs;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  double* sG = reinterpret_cast<double*>(smraw);
+  const int32_t* sE = reinterpret_cast<const int32_t*>(smraw + C::off_enc);
+  double* su = reinterpret_cast<double*>(smraw + C::off_su);
+  double* sf = reinterpret_cast<double*>(smraw + C::off_sf);
+  uint64_t* fullG = reinterpret_cast<uint64_t*>(smraw + C::off_bar);
+  uint64_t* fullE = fullG + R;
+
+  const int tid = threadIdx.x;
+  const int cl = tid / n;
+  const int k = tid - cl * n;
+  const bool in_block = cl < CPB;
+  const int cls = in_block ? cl : 0;
+  const int my_nb = ((int)blockIdx.x < nbatch) ? (nbatch - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int total_planes = my_nb * n;
+
+  uint64_t pol = 0;
+  if (tid == 0)
+  {
+    for (int s = 0; s < R + 1; ++s)
+      mbar_init(&fullG[s], 1);
+    mbar_fence_init();
+    pol = policy_evict_first();
+  }
+  __syncthreads();
+
+  // producer state (thread 0 only): next plane to issue
+  int issue_t = 0;
+  auto issue_plane = [&](int t)
+  {
+    const int it = t / n, i = t - it * n;
+    const long long gb = batch0 + blockIdx.x + (long long)it * gridDim.x;
+    const int s = t % R;
+    mbar_expect_tx(&fullG[s], C::plane_bytes);
+    bulk_g2s(sG + (size_t)s * C::plane_doubles, G + (gb * n2 + (long long)i * n) * 6 * S, C::plane_bytes,
+             &fullG[s], pol);
+  };
+  auto issue_enc = [&](int it)
+  {
+    const long long gb = batch0 + blockIdx.x + (long long)it * gridDim.x;
+    mbar_expect_tx(fullE, C::enc_bytes);
+    bulk_g2s(const_cast<int32_t*>(sE), enc + gb * (long long)(n2 * S), C::enc_bytes, fullE, pol);
+  };
+  if (tid == 0 && my_nb > 0)
+  {
+    issue_enc(0);
+    for (; issue_t < R && issue_t < total_planes; ++issue_t)
+      issue_plane(issue_t);
+  }
+
+  double Dk[n], DTk[n];
+#pragma unroll
+  for (int l = 0; l < n; ++l)
+  {
+    Dk[l] = c_D[P][k * n + l];
+    DTk[l] = c_D[P][l * n + k];
+  }
+
+  int stage = 0;
+  uint32_t stage_parity = 0;
+  for (int it = 0; it < my_nb; ++it)
+  {
+    const int b = blockIdx.x + it * gridDim.x;
+    const int pl = b * CPB + cl;
+    const bool active = in_block && pl < count;
+
+    mbar_wait(fullE, it & 1);
+    int d[n2];
+    double u[n2];
+#pragma unroll
+    for (int a = 0; a < n2; ++a)
+      d[a] = sE[a * S + tid];
+    double kap = 0.0;
+    if (active)
+    {
+      kap = kappa[perm[cell0 + pl]];
+#pragma unroll
+      for (int a = 0; a < n2; ++a)
+      {
+        const int idx = d[a] < 0 ? ~d[a] : d[a];
+        const double xv = x[idx];
+        if (d[a] < 0)
+          y[idx] = xv; // Dirichlet row: y = x (src/laplacian.hpp:273-274)
+        u[a] = d[a] < 0 ? 0.0 : xv;
+      }
+    }
+    else
+    {
+#pragma unroll
+      for (int a = 0; a < n2; ++a)
+        u[a] = 0.0;
+    }
+    if (in_block)
+    {
+#pragma unroll
+      for (int j = 0; j < n; ++j)
+        su[cl * CS + j * KP + k] = u[j];
+    }
+    __syncthreads(); // dofmap buffer is free again, z-rows of plane 0 are visible
+    if (tid == 0 && it + 1 < my_nb)
+      issue_enc(it + 1);
+
+    double acc[n2];
+#pragma unroll
+    for (int a = 0; a < n2; ++a)
+      acc[a] = 0.0;
+
+#pragma unroll
+    for (int i = 0; i < n; ++i)
+    {
+      mbar_wait(&fullG[stage], stage_parity);
+      const double* gs = sG + (size_t)stage * C::plane_doubles + tid;
+      const double* sup = su + ((i & 1) * CPB + cls) * CS;
+      double* sfz = sf + ((i & 1) * CPB + cls) * CS;
+      double fz[n];
+#pragma unroll
+      for (int j = 0; j < n; ++j)
+      {
+        double gx = 0.0, gy = 0.0, gz = 0.0;
+        const double2* row = reinterpret_cast<const double2*>(sup + j * KP);
+#pragma unroll
+        for (int l2 = 0; l2 < KP / 2; ++l2)
+        {
+          const double2 r = row[l2];
+          gz = fma(Dk[2 * l2], r.x, gz);
+          if (2 * l2 + 1 < n)
+            gz = fma(Dk[2 * l2 + 1], r.y, gz);
+        }
+#pragma unroll
+        for (int l = 0; l < n; ++l)
+        {
+          gx = fma(c_D[P][i * n + l], u[l * n + j], gx);
+          gy = fma(c_D[P][j * n + l], u[i * n + l], gy);
+        }
+        const double g0 = gs[(j * 6 + 0) * S], g1 = gs[(j * 6 + 1) * S], g2 = gs[(j * 6 + 2) * S];
+        const double g3 = gs[(j * 6 + 3) * S], g4 = gs[(j * 6 + 4) * S], g5 = gs[(j * 6 + 5) * S];
+        const double fx = kap * (g0 * gx + g1 * gy + g2 * gz);
+        const double fy = kap * (g1 * gx + g3 * gy + g4 * gz);
+        fz[j] = kap * (g2 * gx + g4 * gy + g5 * gz);
+#pragma unroll
+        for (int l = 0; l < n; ++l)
+        {
+          acc[l * n + j] = fma(c_D[P][i * n + l], fx, acc[l * n + j]);
+          acc[i * n + l] = fma(c_D[P][j * n + l], fy, acc[i * n + l]);
+        }
+      }
+      if (in_block)
+      {
+#pragma unroll
+        for (int j = 0; j < n; ++j)
+          sfz[j * KP + k] = fz[j];
+        if (i + 1 < n)
+        {
+          double* sun = su + (((i + 1) & 1) * CPB + cl) * CS;
+#pragma unroll
+          for (int j = 0; j < n; ++j)
+            sun[j * KP + k] = u[(i + 1) * n + j];
+        }
+      }
+      __syncthreads(); // geometry stage is consumed; fz rows and next z-rows are visible
+      if (tid == 0)
+      {
+        if (issue_t < total_planes)
+          issue_plane(issue_t++);
+      }
+      if (++stage == R)
+      {
+        stage = 0;
+        stage_parity ^= 1u;
+      }
+#pragma unroll
+      for (int j = 0; j < n; ++j)
+      {
+        const double2* row = reinterpret_cast<const double2*>(sfz + j * KP);
+        double t = 0.0;
+#pragma unroll
+        for (int q2 = 0; q2 < KP / 2; ++q2)
+        {
+          const double2 r = row[q2];
+          t = fma(DTk[2 * q2], r.x, t);
+          if (2 * q2 + 1 < n)
+            t = fma(DTk[2 * q2 + 1], r.y, t);
+        }
+        acc[i * n + j] += t;
+      }
+    }
+    if (active)
+    {
+#pragma unroll
+      for (int a = 0; a < n2; ++a)
+        if (d[a] >= 0)
+          atomicAdd(&y[d[a]], acc[a]);
+    }
+  }
+}
+
+template <int P>
+struct TmaTune
+{
+  static constexpr int R = (P == 4 || P == 1) ? 2 : 3;     // geometry planes in flight per CTA
+  static constexpr int MINB = P == 1 ? 4 : (P == 2 ? 3 : 2); // resident CTAs per SM
+};
+
+template <int P>
+void launch_apply_tma(pmgx_ctx* c, const double* x, double* y, const double* G, const int32_t* enc,
+                      const int32_t* perm, const double* kappa, long long batch0, int cell0, int count)
+{
+  if (count <= 0)
+    return;
+  constexpr int R = TmaTune<P>::R, MINB = TmaTune<P>::MINB;
+  using C = TmaCfg<P, R>;
+  static bool configured[64] = {false};
+  if (!configured[c->device])
+  {
+    PMGX_CUDA(cudaFuncSetAttribute(k_apply_tma<P, R, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)C::smem));
+    configured[c->device] = true;
+  }
+  const int nbatch = (count + C::cpb - 1) / C::cpb;
+  const int grid = std::min(nbatch, MINB * c->num_sms);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (c->profiling)
+  {
+    PMGX_CUDA(cudaEventCreate(&e0));
+    PMGX_CUDA(cudaEventCreate(&e1));
+    PMGX_CUDA(cudaEventRecord(e0, c->stream));
+  }
+  k_apply_tma<P, R, MINB><<<grid, C::tpb, C::smem, c->stream>>>(x, y, G, enc, perm, kappa, batch0, cell0, count,
+                                                              nbatch);
+  check_launch("k_apply_tma");
+  count_launch(c);
+  if (c->profiling)
+  {
+    PMGX_CUDA(cudaEventRecord(e1, c->stream));
+    c->prof[P].emplace_back(e0, e1);
+  }
+}
+
 void upload_tables(pmgx_ctx* c)
 {
   static double hD[PMGX_MAX_DEGREE + 1][MAXN * MAXN];
@@ -525,8 +1095,10 @@ struct Laplacian : pmgx_operator
   const int32_t* geom_dofmap = nullptr;
   int flags = 0;
   DevBuf<int32_t> perm; // launch position -> caller cell index (lcells then bcells)
-  DevBuf<int32_t> enc;  // [n_list][n3] BC-encoded dofmap
-  DevBuf<double> G;     // [n_list][6][n3]
+  DevBuf<int32_t> enc;  // BC-encoded dofmap, layout `lay`
+  DevBuf<double> G;     // geometry factors, layout `lay`
+  Lay lay;
+  bool use_tma = true; // TMA-pipelined slab kernel (default); PMGX_APPLY_KERNEL=slab|column for A/B runs
 
   int n_list() const { return n_l + n_b; }
 
@@ -537,10 +1109,29 @@ struct Laplacian : pmgx_operator
     PMGX_CUDA(cudaMemsetAsync(y, 0, (size_t)ntot * sizeof(double), ctx->stream)); // out.set(0) :466
     if (halo)
       halo_fwd_begin(halo, x);                                                    // :378
-    launch_apply<PP>(ctx, x, y, G.p, enc.p, perm.p, kappa, 0, n_l);               // :406-409
+    if constexpr (PP <= SLAB_MAX_DEGREE)
+    {
+      if (lay.mode == 1 && use_tma)
+      {
+        launch_apply_tma<PP>(ctx, x, y, G.p, enc.p, perm.p, kappa, 0, 0, n_l);    // :406-409
+        if (halo)
+          halo_fwd_end(halo, x);                                                  // :425
+        launch_apply_tma<PP>(ctx, x, y, G.p, enc.p, perm.p, kappa, lay.nb_l, n_l, n_b); // :449-452
+        return;
+      }
+      if (lay.mode == 1)
+      {
+        launch_apply_slab<PP>(ctx, x, y, G.p, enc.p, perm.p, kappa, 0, 0, n_l);
+        if (halo)
+          halo_fwd_end(halo, x);
+        launch_apply_slab<PP>(ctx, x, y, G.p, enc.p, perm.p, kappa, lay.nb_l, n_l, n_b);
+        return;
+      }
+    }
+    launch_apply<PP>(ctx, x, y, G.p, enc.p, perm.p, kappa, 0, n_l);
     if (halo)
-      halo_fwd_end(halo, x);                                                      // :425
-    launch_apply<PP>(ctx, x, y, G.p, enc.p, perm.p, kappa, n_l, n_b);             // :449-452
+      halo_fwd_end(halo, x);
+    launch_apply<PP>(ctx, x, y, G.p, enc.p, perm.p, kappa, n_l, n_b);
   }
 
   void apply(double* x, double* y) override
@@ -621,16 +1212,31 @@ int pmgx_laplacian_create(pmgx_ctx* ctx, int degree, int n_cells, const int32_t*
   L->perm.upload(perm_h.data(), perm_h.size(), ctx->stream);
 
   const long long total = (long long)n_list * L->n3;
-  L->enc.alloc((size_t)total);
-  L->G.alloc((size_t)total * 6);
+  pmgx::Lay& lay = L->lay;
+  lay.n = n, lay.n2 = n * n, lay.n3 = L->n3;
+  lay.n_l = n_lcells;
+  const char* force = getenv("PMGX_APPLY_KERNEL"); // "column" forces the column kernel (A/B runs)
+  lay.mode = (degree <= pmgx::SLAB_MAX_DEGREE && !(force && std::strcmp(force, "column") == 0)) ? 1 : 0;
+  L->use_tma = !(force && std::strcmp(force, "slab") == 0);
+  lay.cpb = 128 / n, lay.S = 128;
+  lay.nb_l = (n_lcells + lay.cpb - 1) / lay.cpb;
+  lay.n_batches = lay.nb_l + (n_bcells + lay.cpb - 1) / lay.cpb;
+  const long long enc_size = lay.mode == 1 ? lay.enc_size() : total;
+  L->enc.alloc((size_t)enc_size);
+  L->G.alloc((size_t)enc_size * 6);
+  if (lay.mode == 1 && enc_size > 0)
+  { // padded slots: inert
+    PMGX_CUDA(cudaMemsetAsync(L->enc.p, 0, (size_t)enc_size * sizeof(int32_t), ctx->stream));
+    PMGX_CUDA(cudaMemsetAsync(L->G.p, 0, (size_t)enc_size * 6 * sizeof(double), ctx->stream));
+  }
   if (total > 0)
   {
     pmgx::k_encode_dofmap<<<pmgx::setup_grid(ctx, total), 256, 0, ctx->stream>>>(
-        dofmap, L->perm.p, bc_marker, L->enc.p, L->n3, total);
+        dofmap, L->perm.p, bc_marker, L->enc.p, L->n3, total, lay);
     pmgx::check_launch("k_encode_dofmap");
     pmgx::k_geometry<true><<<pmgx::setup_grid(ctx, total), 256, 0, ctx->stream>>>(
         degree, xgeom, geom_dofmap, L->perm.p, L->G.p, nullptr, n_list,
-        (flags & PMGX_LAP_LITERAL_DETJ) != 0);
+        (flags & PMGX_LAP_LITERAL_DETJ) != 0, lay);
     pmgx::check_launch("k_geometry");
     pmgx::count_launch(ctx, 2);
   }
@@ -643,7 +1249,7 @@ int pmgx_laplacian_create(pmgx_ctx* ctx, int degree, int n_cells, const int32_t*
     if (total > 0)
     {
       pmgx::k_diag<<<pmgx::setup_grid(ctx, total), 256, 0, ctx->stream>>>(
-          degree, L->G.p, L->enc.p, L->perm.p, kappa, diag.p, n_list);
+          degree, L->G.p, L->enc.p, L->perm.p, kappa, diag.p, n_list, lay);
       pmgx::check_launch("k_diag");
     }
     pmgx::k_invert_diag<<<(n_owned + 255) / 256, 256, 0, ctx->stream>>>(diag.p, bc_marker,
@@ -669,7 +1275,7 @@ int pmgx_laplacian_get_G(pmgx_operator* op, double* G_out)
   {
     PMGX_CUDA(cudaSetDevice(L->ctx->device));
     pmgx::k_G_to_reference_layout<<<pmgx::setup_grid(L->ctx, total), 256, 0, L->ctx->stream>>>(
-        L->G.p, G_out, L->n3, total);
+        L->G.p, G_out, L->n3, total, L->lay);
     pmgx::check_launch("k_G_to_reference_layout");
     pmgx::count_launch(L->ctx);
   }
@@ -691,9 +1297,9 @@ int pmgx_laplacian_rhs(pmgx_operator* op, const double* fvals, double g, double*
     pmgx::DevBuf<double> dw;
     dw.alloc((size_t)total);
     pmgx::k_geometry<false><<<pmgx::setup_grid(ctx, total), 256, 0, ctx->stream>>>(
-        L->P, L->xgeom, L->geom_dofmap, L->perm.p, nullptr, dw.p, L->n_list(), false);
+        L->P, L->xgeom, L->geom_dofmap, L->perm.p, nullptr, dw.p, L->n_list(), false, L->lay);
     pmgx::check_launch("k_geometry(detJ)");
-    pmgx::k_rhs<<<pmgx::setup_grid(ctx, total), 256, 0, ctx->stream>>>(dw.p, L->enc.p, fvals, b, total);
+    pmgx::k_rhs<<<pmgx::setup_grid(ctx, total), 256, 0, ctx->stream>>>(dw.p, L->enc.p, fvals, b, total, L->n3, L->lay);
     pmgx::check_launch("k_rhs");
     pmgx::count_launch(ctx, 2);
     PMGX_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -727,7 +1333,7 @@ int pmgx_csr_from_laplacian(pmgx_operator* op, pmgx_operator** out)
   if (n_list > 0)
   {
     pmgx::k_element_triplets<<<pmgx::setup_grid(ctx, n_list * per_cell), 256, 0, st>>>(
-        L->P, L->G.p, L->enc.p, L->perm.p, L->kappa, n_list, n_owned, ntot, keys.p, vals.p);
+        L->P, L->G.p, L->enc.p, L->perm.p, L->kappa, n_list, n_owned, ntot, keys.p, vals.p, L->lay);
     pmgx::check_launch("k_element_triplets");
   }
   if (n_owned > 0)
