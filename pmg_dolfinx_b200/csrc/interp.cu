@@ -51,7 +51,9 @@ __device__ __forceinline__ void contract_axis(const double* __restrict__ in, dou
   }
 }
 
-// Prolongation: fine[dofs_f[j]] = sum_k M[j,k] coarse[dofs_c[k]] (overwrite; :21-45)
+// One warp per cell (grid-stride over the cell list): the three 1-D passes run warp-synchronously
+// on a private shared-memory slice, so there is no block barrier and a CTA keeps several cells
+// in flight.  Prolongation: fine[dofs_f[j]] = sum_k M[j,k] coarse[dofs_c[k]] (overwrite; :21-45)
 __global__ void __launch_bounds__(IT)
 k_prolong(int nc, int nf, const double* __restrict__ M1, const int32_t* __restrict__ cells,
           int first, int count, const int32_t* __restrict__ dm_c, const int32_t* __restrict__ dm_f,
@@ -59,26 +61,28 @@ k_prolong(int nc, int nf, const double* __restrict__ M1, const int32_t* __restri
 {
   extern __shared__ double sm[];
   const int nc3 = nc * nc * nc, nf3 = nf * nf * nf;
-  double* sM = sm;               // nf*nc
-  double* b0 = sM + nf * nc;     // nf3
-  double* b1 = b0 + nf3;         // nf3
-  for (int t = threadIdx.x; t < nf * nc; t += IT)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  double* sM = sm;                            // nf*nc
+  double* b0 = sM + nf * nc + warp * 2 * nf3; // nf3 per warp
+  double* b1 = b0 + nf3;
+  for (int t = threadIdx.x; t < nf * nc; t += blockDim.x)
     sM[t] = M1[t];
-  for (int ci = blockIdx.x; ci < count; ci += gridDim.x)
+  __syncthreads();
+  for (long long ci = (long long)blockIdx.x * wpb + warp; ci < count; ci += (long long)gridDim.x * wpb)
   {
     const long long cell = cells[first + ci];
-    __syncthreads();
-    for (int t = threadIdx.x; t < nc3; t += IT)
+    for (int t = lane; t < nc3; t += 32)
       b0[t] = xc[dm_c[cell * nc3 + t]];
-    __syncthreads();
-    contract_axis<false>(b0, b1, sM, nc, nc, nc, 2, nf, threadIdx.x, IT); // [nc][nc][nf]
-    __syncthreads();
-    contract_axis<false>(b1, b0, sM, nc, nc, nf, 1, nf, threadIdx.x, IT); // [nc][nf][nf]
-    __syncthreads();
-    contract_axis<false>(b0, b1, sM, nc, nf, nf, 0, nf, threadIdx.x, IT); // [nf][nf][nf]
-    __syncthreads();
-    for (int t = threadIdx.x; t < nf3; t += IT)
+    __syncwarp();
+    contract_axis<false>(b0, b1, sM, nc, nc, nc, 2, nf, lane, 32); // [nc][nc][nf]
+    __syncwarp();
+    contract_axis<false>(b1, b0, sM, nc, nc, nf, 1, nf, lane, 32); // [nc][nf][nf]
+    __syncwarp();
+    contract_axis<false>(b0, b1, sM, nc, nf, nf, 0, nf, lane, 32); // [nf][nf][nf]
+    __syncwarp();
+    for (int t = lane; t < nf3; t += 32)
       xf[dm_f[cell * nf3 + t]] = b1[t];
+    __syncwarp();
   }
 }
 
@@ -90,29 +94,31 @@ k_restrict(int nc, int nf, const double* __restrict__ M1, const int32_t* __restr
 {
   extern __shared__ double sm[];
   const int nc3 = nc * nc * nc, nf3 = nf * nf * nf;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   double* sM = sm;
-  double* b0 = sM + nf * nc;
+  double* b0 = sM + nf * nc + warp * 2 * nf3;
   double* b1 = b0 + nf3;
-  for (int t = threadIdx.x; t < nf * nc; t += IT)
+  for (int t = threadIdx.x; t < nf * nc; t += blockDim.x)
     sM[t] = M1[t];
-  for (int ci = blockIdx.x; ci < count; ci += gridDim.x)
+  __syncthreads();
+  for (long long ci = (long long)blockIdx.x * wpb + warp; ci < count; ci += (long long)gridDim.x * wpb)
   {
     const long long cell = cells[first + ci];
-    __syncthreads();
-    for (int t = threadIdx.x; t < nf3; t += IT)
+    for (int t = lane; t < nf3; t += 32)
     {
       const int32_t d = dm_f[cell * nf3 + t];
       b0[t] = xf[d] * inv_mult[d];
     }
-    __syncthreads();
-    contract_axis<true>(b0, b1, sM, nf, nf, nf, 0, nc, threadIdx.x, IT); // [nc][nf][nf]
-    __syncthreads();
-    contract_axis<true>(b1, b0, sM, nc, nf, nf, 1, nc, threadIdx.x, IT); // [nc][nc][nf]
-    __syncthreads();
-    contract_axis<true>(b0, b1, sM, nc, nc, nf, 2, nc, threadIdx.x, IT); // [nc][nc][nc]
-    __syncthreads();
-    for (int t = threadIdx.x; t < nc3; t += IT)
+    __syncwarp();
+    contract_axis<true>(b0, b1, sM, nf, nf, nf, 0, nc, lane, 32); // [nc][nf][nf]
+    __syncwarp();
+    contract_axis<true>(b1, b0, sM, nc, nf, nf, 1, nc, lane, 32); // [nc][nc][nf]
+    __syncwarp();
+    contract_axis<true>(b0, b1, sM, nc, nc, nf, 2, nc, lane, 32); // [nc][nc][nc]
+    __syncwarp();
+    for (int t = lane; t < nc3; t += 32)
       atomicAdd(&xc[dm_c[cell * nc3 + t]], b1[t]);
+    __syncwarp();
   }
 }
 } // namespace
@@ -130,12 +136,23 @@ struct pmgx_interp
   pmgx::DevBuf<int32_t> cells;   // lcells then bcells
   pmgx::DevBuf<double> M1;       // [nf][nc]
   pmgx::DevBuf<double> inv_mult; // 1 / multiplicity of fine dofs
+  // warps per block: as many as fit ~40 KB of private slices (2 nf^3 doubles each), at most 8
+  int wpb() const
+  {
+    const int nf = pf + 1;
+    return std::max(1, std::min(8, (int)(40960 / (2 * nf * nf * nf * sizeof(double)))));
+  }
+  int tpb() const { return 32 * wpb(); }
   size_t smem() const
   {
     const int nc = pc + 1, nf = pf + 1;
-    return (size_t)(nf * nc + 2 * nf * nf * nf) * sizeof(double);
+    return (size_t)(nf * nc + wpb() * 2 * nf * nf * nf) * sizeof(double);
   }
-  int grid(int count) const { return std::max(1, std::min(count, ctx->num_sms * 8)); }
+  int grid(int count) const
+  {
+    const int blocks = (count + wpb() - 1) / wpb();
+    return std::max(1, std::min(blocks, ctx->num_sms * 16));
+  }
 };
 
 extern "C"
@@ -214,7 +231,7 @@ int pmgx_interp_prolong(pmgx_interp* it, double* coarse, double* fine)
     pmgx::halo_fwd_begin(it->halo_c, coarse);                                        // :202
   if (it->n_l > 0)
   {
-    pmgx::k_prolong<<<it->grid(it->n_l), pmgx::IT, it->smem(), c->stream>>>(
+    pmgx::k_prolong<<<it->grid(it->n_l), it->tpb(), it->smem(), c->stream>>>(
         nc, nf, it->M1.p, it->cells.p, 0, it->n_l, it->dm_c, it->dm_f, coarse, fine); // :208
     pmgx::check_launch("k_prolong");
     pmgx::count_launch(c);
@@ -223,7 +240,7 @@ int pmgx_interp_prolong(pmgx_interp* it, double* coarse, double* fine)
     pmgx::halo_fwd_end(it->halo_c, coarse);                                          // :217
   if (it->n_b > 0)
   {
-    pmgx::k_prolong<<<it->grid(it->n_b), pmgx::IT, it->smem(), c->stream>>>(
+    pmgx::k_prolong<<<it->grid(it->n_b), it->tpb(), it->smem(), c->stream>>>(
         nc, nf, it->M1.p, it->cells.p, it->n_l, it->n_b, it->dm_c, it->dm_f, coarse, fine); // :227
     pmgx::check_launch("k_prolong");
     pmgx::count_launch(c);
@@ -243,7 +260,7 @@ int pmgx_interp_restrict(pmgx_interp* it, double* fine, double* coarse)
   PMGX_CUDA(cudaMemsetAsync(coarse, 0, (size_t)it->n_coarse_total * sizeof(double), c->stream)); // :270
   if (it->n_l > 0)
   {
-    pmgx::k_restrict<<<it->grid(it->n_l), pmgx::IT, it->smem(), c->stream>>>(
+    pmgx::k_restrict<<<it->grid(it->n_l), it->tpb(), it->smem(), c->stream>>>(
         nc, nf, it->M1.p, it->cells.p, 0, it->n_l, it->dm_c, it->dm_f, fine, it->inv_mult.p, coarse);
     pmgx::check_launch("k_restrict");
     pmgx::count_launch(c);
@@ -252,7 +269,7 @@ int pmgx_interp_restrict(pmgx_interp* it, double* fine, double* coarse)
     pmgx::halo_fwd_end(it->halo_f, fine);                                            // :281
   if (it->n_b > 0)
   {
-    pmgx::k_restrict<<<it->grid(it->n_b), pmgx::IT, it->smem(), c->stream>>>(
+    pmgx::k_restrict<<<it->grid(it->n_b), it->tpb(), it->smem(), c->stream>>>(
         nc, nf, it->M1.p, it->cells.p, it->n_l, it->n_b, it->dm_c, it->dm_f, fine, it->inv_mult.p, coarse);
     pmgx::check_launch("k_restrict");
     pmgx::count_launch(c);

@@ -60,10 +60,11 @@ struct Lay
 {
   int mode; // 0 COLUMN, 1 SLAB
   int n, n2, n3;
-  int cpb, S;
+  int cpb, S, SE; // SE: slot stride of the int32 dofmap rows (multiple of 4 -> 16-byte rows)
   int n_l, nb_l;
   long long n_batches;
-  __host__ __device__ long long enc_size() const { return mode == 0 ? 0 : n_batches * n2 * S; }
+  __host__ __device__ long long enc_size() const { return mode == 0 ? 0 : n_batches * n2 * SE; }
+  __host__ __device__ long long g_size() const { return mode == 0 ? 0 : n_batches * n2 * 6 * S; }
   __host__ __device__ long long enc_index(long long p, int a) const
   {
     if (mode == 0)
@@ -71,7 +72,7 @@ struct Lay
     const long long pl = p < n_l ? p : p - n_l;
     const long long batch = (p < n_l ? 0 : nb_l) + pl / cpb;
     const int slot = (int)(pl % cpb) * n + a % n;
-    return (batch * n2 + a / n) * S + slot;
+    return (batch * n2 + a / n) * SE + slot;
   }
   __host__ __device__ long long g_index(long long p, int comp, int q) const
   {
@@ -536,7 +537,8 @@ struct SlabCfg
   static constexpr int n2 = n * n;
   static constexpr int tpb = 128;
   static constexpr int cpb = tpb / n;      // cells per block
-  static constexpr int S = tpb;            // slots per (batch, ix, iy) row of G / enc
+  static constexpr int S = (cpb * n + 1) & ~1; // slots per (batch, ix, iy) row of G
+  static constexpr int SE = (cpb * n + 3) & ~3; // ... and of the dofmap
   static constexpr int kp = n + (n & 1);   // padded z-row (16-byte rows for double2 loads)
   static constexpr int su_doubles = cpb * n2 * kp;
   static constexpr int sf_doubles = 2 * cpb * n * kp;
@@ -550,7 +552,7 @@ k_apply_slab(const double* __restrict__ x, double* __restrict__ y, const double*
              const double* __restrict__ kappa, long long batch0, int cell0, int count)
 {
   using C = SlabCfg<P>;
-  constexpr int n = C::n, n2 = C::n2, CPB = C::cpb, S = C::S, KP = C::kp;
+  constexpr int n = C::n, n2 = C::n2, CPB = C::cpb, S = C::S, SE = C::SE, KP = C::kp;
   extern __shared__ __align__(16) double smem[];
   double* su = smem;                  // [CPB][n2][KP]
   double* sf = smem + C::su_doubles;  // [2][CPB][n][KP]
@@ -562,7 +564,7 @@ k_apply_slab(const double* __restrict__ x, double* __restrict__ y, const double*
   const bool in_block = cl < CPB;
   const bool active = in_block && pl < count;
   const long long gb = batch0 + blockIdx.x;
-  const int32_t* e = enc + gb * (n2 * S) + tid;
+  const int32_t* e = enc + gb * (n2 * SE) + tid;
   const double* g = G + gb * ((long long)n2 * 6 * S) + tid;
   const int cls = in_block ? cl : 0;
 
@@ -573,7 +575,7 @@ k_apply_slab(const double* __restrict__ x, double* __restrict__ y, const double*
   {
 #pragma unroll
     for (int a = 0; a < n2; ++a)
-      d[a] = ldg_stream_i32(e + a * S);
+      d[a] = ldg_stream_i32(e + a * SE);
     kap = kappa[perm[cell0 + pl]];
 #pragma unroll
     for (int a = 0; a < n2; ++a)
@@ -784,14 +786,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
-template <int P, int R>
+template <int P, int TPB, int R>
 struct TmaCfg
 {
   static constexpr int n = P + 1;
   static constexpr int n2 = n * n;
-  static constexpr int tpb = 128;
-  static constexpr int S = tpb;
+  static constexpr int tpb = TPB;
   static constexpr int cpb = tpb / n;
+  static constexpr int S = (cpb * n + 1) & ~1;  // G rows: 16-byte multiples, (almost) no padding streamed
+  static constexpr int SE = (cpb * n + 3) & ~3; // dofmap rows: 16-byte multiples of int32
+  static constexpr int minb = P == 1 ? 4 : (P == 2 ? 3 : (TPB <= 64 ? 4 : 2)); // resident CTAs per SM
   static constexpr int kp = n + (n & 1);
   // per-cell stride of a z-row plane buffer: an odd number of 16-byte chunks, so the cells of
   // a warp start in different bank groups (profiles/r1_apply_p3_slab.txt: 75 % of the shared
@@ -799,7 +803,7 @@ struct TmaCfg
   static constexpr int cs = ((n * kp / 2) & 1) ? n * kp : n * kp + 2;
   static constexpr int plane_doubles = n * 6 * S;
   static constexpr uint32_t plane_bytes = plane_doubles * sizeof(double);
-  static constexpr uint32_t enc_bytes = n2 * S * sizeof(int32_t);
+  static constexpr uint32_t enc_bytes = n2 * SE * sizeof(int32_t);
   static constexpr int buf_doubles = 2 * cpb * cs; // double-buffered plane rows (su and sf each)
   static constexpr size_t off_enc = (size_t)R * plane_bytes;
   static constexpr size_t off_su = off_enc + enc_bytes;
@@ -808,14 +812,14 @@ struct TmaCfg
   static constexpr size_t smem = off_bar + (R + 1) * sizeof(uint64_t);
 };
 
-template <int P, int R, int MINB>
-__global__ void __launch_bounds__(TmaCfg<P, R>::tpb, MINB)
+template <int P, int TPB, int R>
+__global__ void __launch_bounds__(TPB, TmaCfg<P, TPB, R>::minb)
 k_apply_tma(const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ G,
             const int32_t* __restrict__ enc, const int32_t* __restrict__ perm,
             const double* __restrict__ kappa, long long batch0, int cell0, int count, int nbatch)
 {
-  using C = TmaCfg<P, R>;
-  constexpr int n = C::n, n2 = C::n2, CPB = C::cpb, S = C::S, KP = C::kp, CS = C::cs;
+  using C = TmaCfg<P, TPB, R>;
+  constexpr int n = C::n, n2 = C::n2, CPB = C::cpb, S = C::S, SE = C::SE, KP = C::kp, CS = C::cs;
   extern __shared__ __align__(128) unsigned char smraw[];
   double* sG = reinterpret_cast<double*>(smraw);
   const int32_t* sE = reinterpret_cast<const int32_t*>(smraw + C::off_enc);
@@ -857,7 +861,7 @@ k_apply_tma(const double* __restrict__ x, double* __restrict__ y, const double* 
   {
     const long long gb = batch0 + blockIdx.x + (long long)it * gridDim.x;
     mbar_expect_tx(fullE, C::enc_bytes);
-    bulk_g2s(const_cast<int32_t*>(sE), enc + gb * (long long)(n2 * S), C::enc_bytes, fullE, pol);
+    bulk_g2s(const_cast<int32_t*>(sE), enc + gb * (long long)(n2 * SE), C::enc_bytes, fullE, pol);
   };
   if (tid == 0 && my_nb > 0)
   {
@@ -887,7 +891,7 @@ k_apply_tma(const double* __restrict__ x, double* __restrict__ y, const double* 
     double u[n2];
 #pragma unroll
     for (int a = 0; a < n2; ++a)
-      d[a] = sE[a * S + tid];
+      d[a] = sE[a * SE + tid];
     double kap = 0.0;
     if (active)
     {
@@ -1012,30 +1016,24 @@ k_apply_tma(const double* __restrict__ x, double* __restrict__ y, const double* 
   }
 }
 
-template <int P>
-struct TmaTune
+template <int P, int TPB, int R>
+void launch_apply_tma_t(pmgx_ctx* c, const double* x, double* y, const double* G, const int32_t* enc,
+                        const int32_t* perm, const double* kappa, long long batch0, int cell0, int count)
 {
-  static constexpr int R = (P == 4 || P == 1) ? 2 : 3;     // geometry planes in flight per CTA
-  static constexpr int MINB = P == 1 ? 4 : (P == 2 ? 3 : 2); // resident CTAs per SM
-};
-
-template <int P>
-void launch_apply_tma(pmgx_ctx* c, const double* x, double* y, const double* G, const int32_t* enc,
-                      const int32_t* perm, const double* kappa, long long batch0, int cell0, int count)
-{
-  if (count <= 0)
-    return;
-  constexpr int R = TmaTune<P>::R, MINB = TmaTune<P>::MINB;
-  using C = TmaCfg<P, R>;
-  static bool configured[64] = {false};
-  if (!configured[c->device])
+  using C = TmaCfg<P, TPB, R>;
+  static int ctas_per_sm[64] = {0};
+  if (ctas_per_sm[c->device] == 0)
   {
-    PMGX_CUDA(cudaFuncSetAttribute(k_apply_tma<P, R, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PMGX_CUDA(cudaFuncSetAttribute(k_apply_tma<P, TPB, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)C::smem));
-    configured[c->device] = true;
+    int nb = 0;
+    PMGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_apply_tma<P, TPB, R>, TPB, C::smem));
+    PMGX_REQUIRE(nb >= 1, "k_apply_tma<%d,%d,%d> does not fit on an SM", P, TPB, R);
+    ctas_per_sm[c->device] = nb;
   }
   const int nbatch = (count + C::cpb - 1) / C::cpb;
-  const int grid = std::min(nbatch, MINB * c->num_sms);
+  // persistent CTAs: exactly the number that is co-resident, so every SM streams all the time
+  const int grid = std::min(nbatch, ctas_per_sm[c->device] * c->num_sms);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (c->profiling)
   {
@@ -1043,8 +1041,7 @@ void launch_apply_tma(pmgx_ctx* c, const double* x, double* y, const double* G, 
     PMGX_CUDA(cudaEventCreate(&e1));
     PMGX_CUDA(cudaEventRecord(e0, c->stream));
   }
-  k_apply_tma<P, R, MINB><<<grid, C::tpb, C::smem, c->stream>>>(x, y, G, enc, perm, kappa, batch0, cell0, count,
-                                                              nbatch);
+  k_apply_tma<P, TPB, R><<<grid, TPB, C::smem, c->stream>>>(x, y, G, enc, perm, kappa, batch0, cell0, count, nbatch);
   check_launch("k_apply_tma");
   count_launch(c);
   if (c->profiling)
@@ -1052,6 +1049,31 @@ void launch_apply_tma(pmgx_ctx* c, const double* x, double* y, const double* G, 
     PMGX_CUDA(cudaEventRecord(e1, c->stream));
     c->prof[P].emplace_back(e0, e1);
   }
+}
+
+// default tuning (threads per CTA, geometry planes in flight); PMGX_TMA_TPB / PMGX_TMA_R override
+// (measured on B200, scripts/sweep_tma.sh: more, smaller CTAs with a 2-plane ring win for P3/P4)
+inline int tma_default_tpb(int P) { return (P == 3 || P == 4) ? 64 : 128; }
+inline int tma_default_r(int P) { return P == 1 ? 3 : 2; }
+
+template <int P>
+void launch_apply_tma(pmgx_ctx* c, int tpb, int r, const double* x, double* y, const double* G,
+                      const int32_t* enc, const int32_t* perm, const double* kappa, long long batch0, int cell0,
+                      int count)
+{
+  if (count <= 0)
+    return;
+#define PMGX_TMA_CASE(T, RR)                                                                       \
+  if (tpb == T && r == RR)                                                                         \
+    return launch_apply_tma_t<P, T, RR>(c, x, y, G, enc, perm, kappa, batch0, cell0, count);
+  PMGX_TMA_CASE(128, 2)
+  PMGX_TMA_CASE(128, 3)
+  PMGX_TMA_CASE(64, 2)
+  PMGX_TMA_CASE(64, 3)
+  PMGX_TMA_CASE(64, 4)
+#undef PMGX_TMA_CASE
+  set_error("unsupported TMA kernel configuration tpb=%d r=%d", tpb, r);
+  throw Error{PMGX_ERR_ARG};
 }
 
 void upload_tables(pmgx_ctx* c)
@@ -1098,6 +1120,7 @@ struct Laplacian : pmgx_operator
   DevBuf<int32_t> enc;  // BC-encoded dofmap, layout `lay`
   DevBuf<double> G;     // geometry factors, layout `lay`
   Lay lay;
+  int tma_tpb = 128, tma_r = 2;
   bool use_tma = true; // TMA-pipelined slab kernel (default); PMGX_APPLY_KERNEL=slab|column for A/B runs
 
   int n_list() const { return n_l + n_b; }
@@ -1113,10 +1136,10 @@ struct Laplacian : pmgx_operator
     {
       if (lay.mode == 1 && use_tma)
       {
-        launch_apply_tma<PP>(ctx, x, y, G.p, enc.p, perm.p, kappa, 0, 0, n_l);    // :406-409
+        launch_apply_tma<PP>(ctx, tma_tpb, tma_r, x, y, G.p, enc.p, perm.p, kappa, 0, 0, n_l); // :406-409
         if (halo)
           halo_fwd_end(halo, x);                                                  // :425
-        launch_apply_tma<PP>(ctx, x, y, G.p, enc.p, perm.p, kappa, lay.nb_l, n_l, n_b); // :449-452
+        launch_apply_tma<PP>(ctx, tma_tpb, tma_r, x, y, G.p, enc.p, perm.p, kappa, lay.nb_l, n_l, n_b); // :449-452
         return;
       }
       if (lay.mode == 1)
@@ -1218,16 +1241,28 @@ int pmgx_laplacian_create(pmgx_ctx* ctx, int degree, int n_cells, const int32_t*
   const char* force = getenv("PMGX_APPLY_KERNEL"); // "column" forces the column kernel (A/B runs)
   lay.mode = (degree <= pmgx::SLAB_MAX_DEGREE && !(force && std::strcmp(force, "column") == 0)) ? 1 : 0;
   L->use_tma = !(force && std::strcmp(force, "slab") == 0);
-  lay.cpb = 128 / n, lay.S = 128;
+  L->tma_tpb = pmgx::tma_default_tpb(degree);
+  L->tma_r = pmgx::tma_default_r(degree);
+  if (const char* e = getenv("PMGX_TMA_TPB"))
+    L->tma_tpb = atoi(e);
+  if (const char* e = getenv("PMGX_TMA_R"))
+    L->tma_r = atoi(e);
+  if (!L->use_tma)
+    L->tma_tpb = 128;
+  PMGX_REQUIRE(L->tma_tpb == 64 || L->tma_tpb == 128, "PMGX_TMA_TPB must be 64 or 128");
+  lay.cpb = L->tma_tpb / n;
+  lay.S = (lay.cpb * n + 1) & ~1;
+  lay.SE = (lay.cpb * n + 3) & ~3;
   lay.nb_l = (n_lcells + lay.cpb - 1) / lay.cpb;
   lay.n_batches = lay.nb_l + (n_bcells + lay.cpb - 1) / lay.cpb;
   const long long enc_size = lay.mode == 1 ? lay.enc_size() : total;
+  const long long g_size = lay.mode == 1 ? lay.g_size() : total * 6;
   L->enc.alloc((size_t)enc_size);
-  L->G.alloc((size_t)enc_size * 6);
+  L->G.alloc((size_t)g_size);
   if (lay.mode == 1 && enc_size > 0)
   { // padded slots: inert
     PMGX_CUDA(cudaMemsetAsync(L->enc.p, 0, (size_t)enc_size * sizeof(int32_t), ctx->stream));
-    PMGX_CUDA(cudaMemsetAsync(L->G.p, 0, (size_t)enc_size * 6 * sizeof(double), ctx->stream));
+    PMGX_CUDA(cudaMemsetAsync(L->G.p, 0, (size_t)g_size * sizeof(double), ctx->stream));
   }
   if (total > 0)
   {
