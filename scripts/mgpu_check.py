@@ -1,0 +1,184 @@
+"""Multi-GPU parity check (run under torchrun, one rank per GPU).
+
+Partitions a small box mesh over the ranks with the product's host partitioner, runs the
+operator apply, Jacobi-CG, Chebyshev and the P4->P2->P1 V-cycle with NCCL halo exchange and
+all-reduced dots, gathers the owned values on rank 0 and compares them with the single-domain
+oracle in the canonical global numbering (result must be partition independent to
+1e-12; histories 1e-10, identical CG iteration counts).  Exit code 0 = pass.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+PGRID = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    backend = os.environ.get("PMGX_CHECK_BACKEND", "nccl")
+    torch.cuda.set_device(local)
+    dist.init_process_group(backend, device_id=torch.device("cuda", local) if backend == "nccl" else None)
+    from pmg_dolfinx_b200 import api
+    box = [api.Context.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    ctx = api.Context(local, rank, world, box[0])
+    n = tuple(int(v) for v in os.environ.get("PMGX_CHECK_MESH", "9,8,7").split(","))
+    perturb = float(os.environ.get("PMGX_CHECK_PERTURB", "0.15"))
+    degrees = (1, 2, 4)
+    mesh = api.BoxMesh(n, PGRID[world], rank, perturb=perturb)
+    # the same perturbed geometry for the oracle: take it from a single-domain product mesh
+    full = api.BoxMesh(n, (1, 1, 1), 0, perturb=perturb)
+
+    def gather_owned(vec, sp):
+        """rank 0 gets the global vector in canonical numbering."""
+        vals = vec.data[: sp.n_owned].cpu().numpy() if hasattr(vec, "data") else vec
+        objs = [None] * world if rank == 0 else None
+        dist.gather_object((sp.l2g[: sp.n_owned], vals), objs, dst=0)
+        if rank != 0:
+            return None
+        out = np.full(sp.n_global, np.nan)
+        for l2g, v in objs:
+            out[l2g] = v
+        assert not np.isnan(out).any()
+        return out
+
+    def scatter_global(gvec, sp, halo):
+        v = api.Vector(ctx, sp.n_owned, sp.n_ghost, halo)
+        loc = np.zeros(sp.n_owned + sp.n_ghost)
+        loc[: sp.n_owned] = gvec[sp.l2g[: sp.n_owned]]
+        v.data.copy_(torch.from_numpy(loc))
+        return v
+
+    xgeom, gdm = ctx.to_device(mesh.xgeom), ctx.to_device(mesh.geom_dofmap)
+    kappa = torch.full((mesh.n_cells,), 2.0, dtype=torch.float64, device=ctx.device)
+    lv = []
+    for P in degrees:
+        sp = mesh.space(P, want_coords=True)
+        halo = api.Halo.from_space(ctx, sp)
+        dm, bc = ctx.to_device(sp.dofmap), ctx.to_device(sp.bc)
+        op = api.MatFreeLaplacian(ctx, P, kappa, dm, xgeom, gdm, mesh.lcells, mesh.bcells, bc, sp.n_owned, sp.n_ghost, halo)
+        lv.append(dict(P=P, sp=sp, halo=halo, dm=dm, bc=bc, op=op))
+
+    # ---------------- oracle on rank 0 (single domain, same geometry)
+    ok = True
+    if rank == 0:
+        from oracle import mesh as om, operator as oo, solvers as osol
+        omesh = om.BoxMesh(n, full.xgeom.copy(), full.geom_dofmap.copy())
+        O = []
+        for P in degrees:
+            dm, bc, nd = om.dofmap(omesh, P), om.bc_marker(omesh, P), om.num_dofs(omesh, P)
+            G, _ = oo.geometry_factors(omesh.verts, omesh.geom_dofmap, P)
+            kap = np.full(omesh.ncells, 2.0)
+            A = (lambda P, dm, G, kap, bc: lambda v: oo.apply(P, dm, G, kap, bc, v))(P, dm, G, kap, bc)
+            O.append(dict(P=P, dm=dm, bc=bc, nd=nd, A=A, dinv=1.0 / oo.diagonal(P, dm, G, kap, bc, nd)))
+
+    def check(name, got, ref, tol):
+        nonlocal ok
+        err = np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-300)
+        good = err <= tol
+        ok = ok and good
+        print(f"[mgpu x{world}] {name:38s} rel err {err:.3e}  {'ok' if good else 'FAIL'}", flush=True)
+
+    rng = np.random.default_rng(42)
+    smoothers, eigs = [], []
+    for li, L in enumerate(lv):
+        sp, P = L["sp"], L["P"]
+        xg = rng.uniform(-1, 1, sp.n_global)
+        x = scatter_global(xg, sp, L["halo"])
+        y = api.Vector(ctx, sp.n_owned, sp.n_ghost)
+        L["op"](x, y)
+        yg = gather_owned(y, sp)
+        dv = api.Vector(ctx, sp.n_owned, sp.n_ghost)
+        L["op"].get_diag_inverse(dv)
+        dg = gather_owned(dv, sp)
+        # CG with b = 1 (examples/pmg/main.cpp:306-330)
+        cg = api.CGSolver(ctx, sp.n_owned, sp.n_ghost)
+        cg.set_max_iterations(20)
+        cg.set_tolerance(1e-6)
+        cg.store_coefficients(True)
+        xs, b1 = api.Vector(ctx, sp.n_owned, sp.n_ghost, L["halo"]), api.Vector(ctx, sp.n_owned, sp.n_ghost)
+        b1.set(1.0)
+        k = cg.solve(L["op"], xs, b1)
+        eig = cg.compute_eigenvalues()
+        r0, hist = cg.history()
+        xsg = gather_owned(xs, sp)
+        s = api.Chebyshev(ctx, sp.n_owned, sp.n_ghost, (0.1 * eig[-1], 1.1 * eig[-1]))
+        s.set_max_iterations(2)
+        smoothers.append(s)
+        eigs.append(eig[-1])
+        if rank == 0:
+            o = O[li]
+            check(f"P{P} apply", yg, o["A"](xg), 1e-12)
+            check(f"P{P} diag inverse", dg, o["dinv"], 1e-13)
+            xo, ko, al, be, ho, r0o = osol.cg(o["A"], o["dinv"], np.zeros(o["nd"]), np.ones(o["nd"]), 20, 1e-6)
+            ok = ok and (k == ko)
+            print(f"[mgpu x{world}] P{P} CG iterations {k} vs oracle {ko}", flush=True)
+            check(f"P{P} CG residual history", hist, ho, 1e-10)
+            check(f"P{P} CG solution", xsg, xo, 1e-9)
+            check(f"P{P} lambda_max", np.array([eig[-1]]), np.array([osol.lanczos_eigenvalues(al, be)[-1]]), 1e-9)
+            o["lmax"] = 1.1 * osol.lanczos_eigenvalues(al, be)[-1]
+
+    # ---------------- V-cycle
+    interps = []
+    for a, b in zip(lv[:-1], lv[1:]):
+        interps.append(api.Interpolator(ctx, a["P"], b["P"], a["dm"], b["dm"], a["sp"].n_owned + a["sp"].n_ghost,
+                                        b["sp"].n_owned + b["sp"].n_ghost, mesh.lcells, mesh.bcells, a["halo"], b["halo"]))
+    A0 = lv[0]["op"].to_csr()
+    coarse = api.CoarseSolverType(ctx, A0, 60, 1e-10)
+    pmg = api.MultigridPreconditioner(ctx, [L["bc"] for L in lv], flags=2)
+    pmg.set_solvers(smoothers)
+    pmg.set_operators([L["op"] for L in lv])
+    pmg.set_interpolators(interps)
+    pmg.set_coarse_solver(coarse)
+    top = lv[-1]
+    sp = top["sp"]
+    X = sp.coords
+    f = 2.0 * np.pi ** 2 * 3 * np.sin(np.pi * X[:, 0]) * np.sin(np.pi * X[:, 1]) * np.sin(np.pi * X[:, 2]) + 1.0 + X[:, 0]
+    bvec = api.Vector(ctx, sp.n_owned, sp.n_ghost, top["halo"])
+    top["op"].assemble_rhs(ctx.to_device(f), 0.0, bvec)
+    bg = gather_owned(bvec, sp)
+    u = api.Vector(ctx, sp.n_owned, sp.n_ghost)
+    if rank == 0:
+        from oracle import mesh as om, operator as oo, solvers as osol
+        olev = [osol.Level(o["A"], o["dinv"], o["bc"].astype(float), o["lmax"], 2) for o in O]
+        pro, res = [], []
+        for a, b in zip(O[:-1], O[1:]):
+            pro.append((lambda a, b: lambda xc: oo.prolong(a["P"], b["P"], a["dm"], b["dm"], xc, b["nd"]))(a, b))
+            res.append((lambda a, b: lambda xf: oo.restrict(a["P"], b["P"], a["dm"], b["dm"], xf, a["nd"]))(a, b))
+        G0, _ = oo.geometry_factors(omesh.verts, omesh.geom_dofmap, degrees[0])
+        A0o = oo.assemble_csr(degrees[0], O[0]["dm"], G0, np.full(omesh.ncells, 2.0), O[0]["bc"], O[0]["nd"])
+        d0 = 1.0 / A0o.diagonal()
+        cso = lambda u0, b0: osol.cg(lambda v: A0o @ v, d0, u0, b0, 60, 1e-10)[0]
+        Xo = om.dof_coords(omesh, degrees[-1])
+        fo = 2.0 * np.pi ** 2 * 3 * np.sin(np.pi * Xo[:, 0]) * np.sin(np.pi * Xo[:, 1]) * np.sin(np.pi * Xo[:, 2]) + 1.0 + Xo[:, 0]
+        bo = oo.rhs_collocated(omesh, degrees[-1], lambda _: fo, O[-1]["bc"])
+        check("rhs assembly", bg, bo, 1e-13)
+        uo = np.zeros(O[-1]["nd"])
+    for it in range(3):
+        rn = pmg.apply(bvec, u, verbose=True)
+        hg = pmg.diagnostics()
+        ug = gather_owned(u, sp)
+        if rank == 0:
+            ho = []
+            uo = osol.vcycle(olev, pro, res, bo, uo, coarse_solve=cso, history=ho)
+            hov = np.array([h[2] for h in ho])
+            good = len(hg) == len(hov) and np.all(np.abs(hg - hov) <= 1e-9 * hov[0])
+            ok = ok and good
+            print(f"[mgpu x{world}] V-cycle {it} stage residuals {'ok' if good else 'FAIL'} (final {rn:.6e} vs {hov[-1]:.6e})", flush=True)
+            check(f"V-cycle {it} solution", ug, uo, 1e-9)
+    flag = torch.tensor([1 if ok else 0], device=ctx.device)
+    dist.broadcast(flag, src=0)
+    ctx.sync()
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print(f"[mgpu x{world}] {'PASS' if ok else 'FAIL'}", flush=True)
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,23 @@
+"""GPU, multi-rank: NCCL halo exchange + all-reduced dots; 2/4/8-GPU == single-domain oracle
+(scripts/mgpu_check.py run under torchrun).  Skipped when fewer than 2 GPUs are visible."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("nranks", [2, 4, 8])
+def test_multi_gpu_matches_oracle(nranks):
+    import torch
+    if not torch.cuda.is_available() or torch.cuda.device_count() < nranks:
+        pytest.skip(f"needs {nranks} GPUs")
+    port = 29600 + nranks
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nranks}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "scripts", "mgpu_check.py")]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert f"[mgpu x{nranks}] PASS" in r.stdout
