@@ -234,6 +234,9 @@ int pmgx_coarse_destroy(pmgx_coarse* cs);
 #define PMGX_VC_DEFAULT 0
 #define PMGX_VC_LITERAL_REFERENCE_BC 1  /* mask b on level 0 only, like src/pmg.hpp:100-103 */
 #define PMGX_VC_DIAGNOSTICS 2           /* evaluate the reference's eager residual norms (quirk Q8) */
+#define PMGX_VC_LITERAL_SEQUENCE 4      /* recompute r = b - A u after pre-smoothing with one more apply and
+                                           run the smoother's A*0 on zero initial guesses, exactly like
+                                           src/pmg.hpp:83-92; default reuses the smoother's residual */
 int pmgx_vcycle_create(pmgx_ctx* ctx, int n_levels, pmgx_operator** ops, pmgx_cheb** smoothers,
                        pmgx_interp** interps, const int8_t** bc_markers, pmgx_coarse* coarse,
                        int flags, pmgx_vcycle** out);

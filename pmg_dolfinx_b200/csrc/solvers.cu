@@ -36,12 +36,12 @@ k_cheb_init(const double* __restrict__ b, const double* __restrict__ q, const do
   double s = 0.0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nth)
   {
-    const double rv = q[i] * (-1.0) + b[i];
+    const double rv = q ? q[i] * (-1.0) + b[i] : b[i]; // q == nullptr: x is known to be zero
     const double zv = (rv * dinv[i]) * c0;
     r[i] = rv;
     z[i] = zv;
     if (add_x)
-      x[i] = zv * 1.0 + x[i];
+      x[i] = q ? zv * 1.0 + x[i] : zv;
     if (NORM)
       s = fma(rv, rv, s);
   }
@@ -102,10 +102,13 @@ k_cg_init(const double* __restrict__ b, const double* __restrict__ y, const doub
 
 // alpha = rnorm / (p.y) ; x += alpha p ; r -= alpha y ; y = D^-1 r ; out = r.y  (cg.hpp:182-195)
 __global__ void __launch_bounds__(FT)
-k_cg_update(double rnorm, const double* __restrict__ pAp, const double* __restrict__ p,
-            const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r,
-            double* __restrict__ y, long long n, double* partials, unsigned int* counter, double* out)
+k_cg_update(double rnorm, const double* __restrict__ rnorm_dev, const double* __restrict__ pAp,
+            const double* __restrict__ p, const double* __restrict__ dinv, double* __restrict__ x,
+            double* __restrict__ r, double* __restrict__ y, long long n, double* partials,
+            unsigned int* counter, double* out)
 {
+  if (rnorm_dev)
+    rnorm = *rnorm_dev; // device-resident variant (no host round trip between iterations)
   const double alpha = rnorm / *pAp;
   const double nalpha = -alpha;
   const long long nth = (long long)gridDim.x * blockDim.x;
@@ -122,6 +125,17 @@ k_cg_update(double rnorm, const double* __restrict__ pAp, const double* __restri
   }
   double v[1] = {s};
   grid_reduce<1>(v, partials, counter, out);
+}
+
+// p = (rn_new / rn_old) p + y with the ratio formed on the device                (cg.hpp:197,211)
+__global__ void __launch_bounds__(FT)
+k_cg_pupdate(const double* __restrict__ rn_new, const double* __restrict__ rn_old,
+             const double* __restrict__ y, double* __restrict__ p, long long n)
+{
+  const double beta = *rn_new / *rn_old;
+  const long long nth = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nth)
+    p[i] = p[i] * beta + y[i];
 }
 
 void check(const char* w) { check_launch(w); }
@@ -141,21 +155,24 @@ struct pmgx_cheb
 namespace pmgx
 {
 // x <- Chebyshev(A, x, b). hist: max_iter+1 residual norms or nullptr.
-void cheb_solve(pmgx_cheb* s, pmgx_operator* A, double* x, const double* b, double* hist)
+void cheb_solve(pmgx_cheb* s, pmgx_operator* A, double* x, const double* b, double* hist,
+                bool x_is_zero = false)
 {
   pmgx_ctx* c = s->ctx;
   const long long n = s->n_owned;
   const double lmax = s->eig_max; // only the upper bound is used (chebyshev.hpp:51)
   const double* dinv = A->diag_inv.p; // get_diag_inverse without the per-call copy (:53)
   const int grid = fused_grid(c, n);
-  A->apply(x, s->q.p); // :56
+  if (!x_is_zero)
+    A->apply(x, s->q.p); // :56
+  const double* q0 = x_is_zero ? nullptr : s->q.p; // A*0 = 0: skip the apply, r = b
   const bool first_add = s->max_iter >= 1;
   const double c0 = 4.0 / (3.0 * lmax);
   if (hist)
-    k_cheb_init<true><<<grid, FT, 0, c->stream>>>(b, s->q.p, dinv, s->r.p, s->z.p, x, c0, first_add, n,
+    k_cheb_init<true><<<grid, FT, 0, c->stream>>>(b, q0, dinv, s->r.p, s->z.p, x, c0, first_add, n,
                                                   c->d_partials, c->d_counter, c->d_scalars + 8);
   else
-    k_cheb_init<false><<<grid, FT, 0, c->stream>>>(b, s->q.p, dinv, s->r.p, s->z.p, x, c0, first_add, n,
+    k_cheb_init<false><<<grid, FT, 0, c->stream>>>(b, q0, dinv, s->r.p, s->z.p, x, c0, first_add, n,
                                                    c->d_partials, c->d_counter, c->d_scalars + 8);
   check("k_cheb_init");
   count_launch(c);
@@ -226,7 +243,7 @@ int cg_solve(pmgx_cg* s, pmgx_operator* A, double* x, const double* b)
     ++k;
     A->apply(s->p.p, s->y.p);                                                    // :179
     vec::dot_device(c, s->p.p, s->y.p, n, 2);                                    // :182
-    k_cg_update<<<grid, FT, 0, c->stream>>>(rnorm, c->d_scalars + 2, s->p.p, dinv, x, s->r.p, s->y.p, n,
+    k_cg_update<<<grid, FT, 0, c->stream>>>(rnorm, nullptr, c->d_scalars + 2, s->p.p, dinv, x, s->r.p, s->y.p, n,
                                             c->d_partials, c->d_counter, c->d_scalars + 3); // :186-195
     check("k_cg_update");
     count_launch(c);
@@ -249,6 +266,57 @@ int cg_solve(pmgx_cg* s, pmgx_operator* A, double* x, const double* b)
       s->betas.push_back(beta);
       s->residuals.push_back(rnorm);
     }
+  }
+  return k;
+}
+} // namespace pmgx
+
+namespace pmgx
+{
+// Same recurrence as cg_solve, but alpha and beta never leave the device: the host only looks
+// at the residual every `check_every` iterations, so an iteration costs launches and two
+// all-reduces, no host round trip.  Used by the coarse solver, where iteration counts are not a
+// parity quantity (the reference runs PETSc CG + BoomerAMG there, src/amg.hpp:33-47).
+int cg_solve_device(pmgx_cg* s, pmgx_operator* A, double* x, const double* b, int check_every)
+{
+  pmgx_ctx* c = s->ctx;
+  const long long n = s->n_owned;
+  const double* dinv = A->diag_inv.p;
+  const int grid = fused_grid(c, n);
+  double* rn = c->d_scalars + 16; // rn[0], rn[1]: ping-pong r.M^-1 r
+  double* pap = c->d_scalars + 18;
+  A->apply(x, s->y.p);
+  k_cg_init<<<grid, FT, 0, c->stream>>>(b, s->y.p, dinv, s->r.p, s->p.p, n, c->d_partials, c->d_counter, rn);
+  check("k_cg_init");
+  count_launch(c);
+  vec::allreduce_scalars(c, 16, 1, false);
+  const double rnorm0 = vec::read_scalar(c, 16);
+  s->rnorm0 = rnorm0;
+  s->history.clear();
+  if (!(rnorm0 > 0.0))
+    return 0;
+  const double rtol2 = s->rtol * s->rtol;
+  int k = 0;
+  while (k < s->max_iter)
+  {
+    const int cur = k & 1, nxt = cur ^ 1;
+    ++k;
+    A->apply(s->p.p, s->y.p);
+    vec::dot_device(c, s->p.p, s->y.p, n, 18);
+    k_cg_update<<<grid, FT, 0, c->stream>>>(0.0, rn + cur, pap, s->p.p, dinv, x, s->r.p, s->y.p, n,
+                                            c->d_partials, c->d_counter, rn + nxt);
+    check("k_cg_update");
+    vec::allreduce_scalars(c, 16 + nxt, 1, false);
+    if (k % check_every == 0 || k == s->max_iter)
+    {
+      const double r = vec::read_scalar(c, 16 + nxt);
+      s->history.push_back(r);
+      if (r / rnorm0 < rtol2)
+        break;
+    }
+    k_cg_pupdate<<<grid, FT, 0, c->stream>>>(rn + nxt, rn + cur, s->y.p, s->p.p, n);
+    check("k_cg_pupdate");
+    count_launch(c, 2);
   }
   return k;
 }
@@ -510,7 +578,7 @@ int pmgx_coarse_solve(pmgx_coarse* cs, double* x, const double* b, int* iters_h)
   PMGX_API_BEGIN
   PMGX_REQUIRE(cs && x && b, "coarse_solve: null argument");
   PMGX_CUDA(cudaSetDevice(cs->ctx->device));
-  const int k = pmgx::cg_solve(cs->cg, cs->A, x, b);
+  const int k = pmgx::cg_solve_device(cs->cg, cs->A, x, b, 8);
   if (iters_h)
     *iters_h = k;
   PMGX_API_END
@@ -578,6 +646,7 @@ int pmgx_vcycle_apply(pmgx_vcycle* v, const double* b_in, double* u_inout, doubl
   const int top = nl - 1;
   const bool diag = (v->flags & PMGX_VC_DIAGNOSTICS) != 0;
   const bool literal_bc = (v->flags & PMGX_VC_LITERAL_REFERENCE_BC) != 0;
+  const bool literal_seq = (v->flags & PMGX_VC_LITERAL_SEQUENCE) != 0;
   v->diagnostics.clear();
   namespace vec = pmgx::vec;
   for (int i = 0; i < top; ++i) // pmg.hpp:63-64
@@ -589,11 +658,24 @@ int pmgx_vcycle_apply(pmgx_vcycle* v, const double* b_in, double* u_inout, doubl
   {
     if (diag)
       v->diagnostics.push_back(pmgx::residual(v, i, true));                       // :76-80
-    pmgx::cheb_solve(v->smoothers[i], v->ops[i], v->u[i].p, v->b[i].p, nullptr);  // :83
-    const double rn = pmgx::residual(v, i, diag);                                 // :86-89
-    if (diag)
-      v->diagnostics.push_back(rn);
-    int rc = pmgx_interp_restrict(v->interps[i - 1], v->r[i].p, v->b[i - 1].p);   // :92
+    // below the top level u is zero on the way down: the smoother's first apply is skipped
+    pmgx::cheb_solve(v->smoothers[i], v->ops[i], v->u[i].p, v->b[i].p, nullptr, !literal_seq && i < top); // :83
+    double* rfine = v->r[i].p;
+    if (literal_seq)
+    {
+      const double rn = pmgx::residual(v, i, diag);                               // :86-89
+      if (diag)
+        v->diagnostics.push_back(rn);
+    }
+    else
+    {
+      // the smoother's recurrence already holds r = b - A u of its final iterate
+      // (src/chebyshev.hpp:73-77); the reference recomputes it with one more apply
+      rfine = v->smoothers[i]->r.p;
+      if (diag)
+        v->diagnostics.push_back(std::sqrt(vec::dot(c, rfine, rfine, v->ops[i]->n_owned)));
+    }
+    int rc = pmgx_interp_restrict(v->interps[i - 1], rfine, v->b[i - 1].p);       // :92
     if (rc != PMGX_OK)
       return rc;
     if (!literal_bc && i - 1 > 0) // quirk Q9: keep Dirichlet rows of intermediate levels clean
@@ -607,7 +689,7 @@ int pmgx_vcycle_apply(pmgx_vcycle* v, const double* b_in, double* u_inout, doubl
       return rc;
   }
   else
-    pmgx::cheb_solve(v->smoothers[0], v->ops[0], v->u[0].p, v->b[0].p, nullptr);  // :109
+    pmgx::cheb_solve(v->smoothers[0], v->ops[0], v->u[0].p, v->b[0].p, nullptr, !literal_seq && nl > 1); // :109
   if (diag)
     v->diagnostics.push_back(pmgx::residual(v, 0, true));                         // :114-117
 
