@@ -33,7 +33,7 @@ namespace pmgx
 namespace
 {
 constexpr int MAXN = PMGX_MAX_DEGREE + 1;
-constexpr int SLAB_MAX_DEGREE = 4; // slab kernel (registers: 2 (P+1)^2 doubles) up to here, column kernel above
+constexpr int SLAB_MAX_DEGREE = 6; // slab kernel (registers: 2 (P+1)^2 doubles) up to here, column kernel above
 
 // 1-D tables for every degree; index [P][...]
 __constant__ double c_D[PMGX_MAX_DEGREE + 1][MAXN * MAXN]; // D[q*n+i] = l_i'(x_q)
@@ -806,10 +806,10 @@ struct TmaCfg
   static constexpr uint32_t enc_bytes = n2 * SE * sizeof(int32_t);
   static constexpr int buf_doubles = 2 * cpb * cs; // double-buffered plane rows (su and sf each)
   static constexpr size_t off_enc = (size_t)R * plane_bytes;
-  static constexpr size_t off_su = off_enc + enc_bytes;
+  static constexpr size_t off_su = off_enc + 2 * enc_bytes; // dofmap double-buffered: read again at scatter time
   static constexpr size_t off_sf = off_su + (size_t)buf_doubles * sizeof(double);
   static constexpr size_t off_bar = off_sf + (size_t)buf_doubles * sizeof(double);
-  static constexpr size_t smem = off_bar + (R + 1) * sizeof(uint64_t);
+  static constexpr size_t smem = off_bar + (R + 2) * sizeof(uint64_t);
 };
 
 template <int P, int TPB, int R>
@@ -839,7 +839,7 @@ k_apply_tma(const double* __restrict__ x, double* __restrict__ y, const double* 
   uint64_t pol = 0;
   if (tid == 0)
   {
-    for (int s = 0; s < R + 1; ++s)
+    for (int s = 0; s < R + 2; ++s)
       mbar_init(&fullG[s], 1);
     mbar_fence_init();
     pol = policy_evict_first();
@@ -860,8 +860,9 @@ k_apply_tma(const double* __restrict__ x, double* __restrict__ y, const double* 
   auto issue_enc = [&](int it)
   {
     const long long gb = batch0 + blockIdx.x + (long long)it * gridDim.x;
-    mbar_expect_tx(fullE, C::enc_bytes);
-    bulk_g2s(const_cast<int32_t*>(sE), enc + gb * (long long)(n2 * SE), C::enc_bytes, fullE, pol);
+    mbar_expect_tx(&fullE[it & 1], C::enc_bytes);
+    bulk_g2s(const_cast<int32_t*>(sE) + (it & 1) * (n2 * SE), enc + gb * (long long)(n2 * SE), C::enc_bytes,
+             &fullE[it & 1], pol);
   };
   if (tid == 0 && my_nb > 0)
   {
@@ -886,12 +887,9 @@ k_apply_tma(const double* __restrict__ x, double* __restrict__ y, const double* 
     const int pl = b * CPB + cl;
     const bool active = in_block && pl < count;
 
-    mbar_wait(fullE, it & 1);
-    int d[n2];
+    mbar_wait(&fullE[it & 1], (it >> 1) & 1);
+    const int32_t* dE = sE + (it & 1) * (n2 * SE) + tid; // this thread's n2 encoded dofs
     double u[n2];
-#pragma unroll
-    for (int a = 0; a < n2; ++a)
-      d[a] = sE[a * SE + tid];
     double kap = 0.0;
     if (active)
     {
@@ -899,11 +897,12 @@ k_apply_tma(const double* __restrict__ x, double* __restrict__ y, const double* 
 #pragma unroll
       for (int a = 0; a < n2; ++a)
       {
-        const int idx = d[a] < 0 ? ~d[a] : d[a];
+        const int da = dE[a * SE];
+        const int idx = da < 0 ? ~da : da;
         const double xv = x[idx];
-        if (d[a] < 0)
+        if (da < 0)
           y[idx] = xv; // Dirichlet row: y = x (src/laplacian.hpp:273-274)
-        u[a] = d[a] < 0 ? 0.0 : xv;
+        u[a] = da < 0 ? 0.0 : xv;
       }
     }
     else
@@ -918,7 +917,7 @@ k_apply_tma(const double* __restrict__ x, double* __restrict__ y, const double* 
       for (int j = 0; j < n; ++j)
         su[cl * CS + j * KP + k] = u[j];
     }
-    __syncthreads(); // dofmap buffer is free again, z-rows of plane 0 are visible
+    __syncthreads(); // z-rows of plane 0 are visible; the other dofmap buffer (batch it-1) is free
     if (tid == 0 && it + 1 < my_nb)
       issue_enc(it + 1);
 
@@ -1010,8 +1009,11 @@ k_apply_tma(const double* __restrict__ x, double* __restrict__ y, const double* 
     {
 #pragma unroll
       for (int a = 0; a < n2; ++a)
-        if (d[a] >= 0)
-          atomicAdd(&y[d[a]], acc[a]);
+      {
+        const int da = dE[a * SE];
+        if (da >= 0)
+          atomicAdd(&y[da], acc[a]);
+      }
     }
   }
 }
@@ -1053,8 +1055,8 @@ void launch_apply_tma_t(pmgx_ctx* c, const double* x, double* y, const double* G
 
 // default tuning (threads per CTA, geometry planes in flight); PMGX_TMA_TPB / PMGX_TMA_R override
 // (measured on B200, scripts/sweep_tma.sh: more, smaller CTAs with a 2-plane ring win for P3/P4)
-inline int tma_default_tpb(int P) { return (P == 3 || P == 4) ? 64 : 128; }
-inline int tma_default_r(int P) { return P == 1 ? 3 : 2; }
+inline int tma_default_tpb(int P) { return (P == 1 || P >= 5) ? 64 : 128; }
+inline int tma_default_r(int P) { return 2; }
 
 template <int P>
 void launch_apply_tma(pmgx_ctx* c, int tpb, int r, const double* x, double* y, const double* G,

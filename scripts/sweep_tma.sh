@@ -1,6 +1,6 @@
 #!/bin/bash
-# sweep TMA kernel tuning (threads per CTA x ring depth) for the slab degrees
-for P in 4 3 2 1; do
+# sweep TMA kernel tuning (threads per CTA x ring depth); usage: sweep_tma.sh "4 3 2 1"
+for P in ${1:-4 3 2 1}; do
   for T in 128 64; do
     for R in 2 3 4; do
       if [ $T = 128 ] && [ $R = 4 ]; then continue; fi
