@@ -46,7 +46,7 @@ int pmgx_ctx_create(int device, int rank, int nranks, const void* nccl_id_h, pmg
   PMGX_CUDA(cudaMalloc(&c->d_scalars, 64 * sizeof(double)));
   PMGX_CUDA(cudaMemset(c->d_scalars, 0, 64 * sizeof(double)));
   PMGX_CUDA(cudaMallocHost(&c->h_scalars, 64 * sizeof(double)));
-  c->max_red_blocks = 4 * c->num_sms;
+  c->max_red_blocks = 8 * c->num_sms;
   PMGX_CUDA(cudaMalloc(&c->d_partials, (size_t)c->max_red_blocks * 4 * sizeof(double)));
   PMGX_CUDA(cudaMalloc(&c->d_counter, 16 * sizeof(unsigned int)));
   PMGX_CUDA(cudaMemset(c->d_counter, 0, 16 * sizeof(unsigned int)));

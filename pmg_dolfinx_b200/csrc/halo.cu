@@ -18,6 +18,13 @@ __global__ void k_pack(int n, const int32_t* __restrict__ idx, const double* __r
   if (i < n)
     out[i] = in[idx[i]];
 }
+__global__ void k_pack_sub(int n, const int32_t* __restrict__ idx, const double* __restrict__ in,
+                           const double* __restrict__ sub, double* __restrict__ out)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    out[i] = sub[idx[i]] * (-1.0) + in[idx[i]];
+}
 __global__ void k_unpack(int n, const int32_t* __restrict__ idx, const double* __restrict__ in,
                          double* __restrict__ out)
 {
@@ -35,7 +42,7 @@ __global__ void k_unpack_add(int n, const int32_t* __restrict__ idx, const doubl
 constexpr int PT = 256;
 } // namespace
 
-void halo_fwd_begin(pmgx_halo* h, double* x)
+void halo_fwd_begin(pmgx_halo* h, double* x, const double* sub)
 {
   pmgx_ctx* c = h->ctx;
   const int ns = h->n_send(), nr = h->n_recv();
@@ -45,7 +52,10 @@ void halo_fwd_begin(pmgx_halo* h, double* x)
   PMGX_CUDA(cudaStreamWaitEvent(c->comm_stream, h->ev_ready, 0));
   if (ns > 0)
   {
-    k_pack<<<(ns + PT - 1) / PT, PT, 0, c->comm_stream>>>(ns, h->send_idx.p, x, h->send_buf.p);
+    if (sub)
+      k_pack_sub<<<(ns + PT - 1) / PT, PT, 0, c->comm_stream>>>(ns, h->send_idx.p, x, sub, h->send_buf.p);
+    else
+      k_pack<<<(ns + PT - 1) / PT, PT, 0, c->comm_stream>>>(ns, h->send_idx.p, x, h->send_buf.p);
     check_launch("k_pack");
     count_launch(c);
   }

@@ -1,17 +1,45 @@
 // p-level prolongation / restriction as batched element-local sum-factorised kernels
 // (north_star item 4).  Replaces interpolate_Q1Q2 / interpolate_Q2Q1 and Interpolator<T>
-// (src/interpolate.hpp:21-87,93-329): one thread block handles a batch of cells, the local
-// operator M = M1d (x) M1d (x) M1d is applied direction by direction in shared memory instead
-// of a per-cell CSR walk by a single thread; cell lists live on the device (no per-call
-// allocation, quirk Q10) and the fine-dof multiplicity is computed on the device.
+// (src/interpolate.hpp:21-87,93-329).
+//
+// Design (not a port of the per-cell CSR walk by one thread): a thread owns one fine z-index k
+// of one cell.  The dofmap rows of the CTA's cells are staged in shared memory with coalesced
+// loads; the z pass reads the coarse values (prolongation) or writes partial sums (restriction)
+// across threads, the y and x passes are register FMAs against the 1-D interpolation table,
+// which is a __grid_constant__ kernel parameter (constant-bank operands).  Every fine dof has a
+// unique writer cell (quirk Q11: the reference lets several cells overwrite shared dofs with
+// equal values), which halves the store traffic and lets u += P u_c be formed in the store.
+// Cell lists live on the device (no per-call allocation, quirk Q10) and the fine-dof
+// multiplicity is computed on the device.
 #include "common.hpp"
 #include "operator.hpp"
+
+#include <cmath>
+#include <cstring>
+#include <type_traits>
 
 namespace pmgx
 {
 namespace
 {
-constexpr int IT = 256;
+struct InterpTab
+{
+  double m[(PMGX_MAX_DEGREE + 1) * (PMGX_MAX_DEGREE + 1)]; // M1[f * NC + c] = l^c_c(x^f_f)
+};
+
+// threads per CTA: the largest of {128, 64, 32} whose staged dofmap rows (+ the restriction's
+// partial sums) stay below the 48 KB static shared-memory limit
+template <int NC, int NF>
+struct XferCfg
+{
+  static constexpr int bytes(int tpb)
+  {
+    const int cpb = tpb / NF;
+    return cpb * (NC * NC * NC + NF * NF * NF) * 4 + cpb * NF * NC * NC * 8;
+  }
+  static constexpr int tpb = bytes(128) <= 46 * 1024 ? 128 : (bytes(64) <= 46 * 1024 ? 64 : 32);
+  static constexpr int cpb = tpb / NF;
+};
 
 __global__ void k_count_mult(const int32_t* __restrict__ dm, long long total, double* __restrict__ mult)
 {
@@ -26,101 +54,218 @@ __global__ void k_invert_mult(double* __restrict__ m, int n)
     m[i] = m[i] > 0.0 ? 1.0 / m[i] : 0.0;
 }
 
-// One tensor direction: out[a0][a1][a2] with the axis `dir` contracted against M.
-//   expand (T=false): out index o in [0,no), in index i in [0,ni): out = sum_i M[o*ni+i] in
-//   reduce (T=true) : out index o in [0,no), in index i in [0,ni): out = sum_i M[i*no+o] in
-// dims: sizes of the three axes of `in`; axis `dir` has size ni and becomes no in `out`.
-template <bool T>
-__device__ __forceinline__ void contract_axis(const double* __restrict__ in, double* __restrict__ out,
-                                              const double* __restrict__ M, int d0, int d1, int d2,
-                                              int dir, int no, int tid, int nthreads)
+// first list position that touches each fine dof ...
+__global__ void k_first_toucher(const int32_t* __restrict__ dm_f, const int32_t* __restrict__ cells,
+                                int nf3, long long total, int32_t* __restrict__ first)
 {
-  const int ni = dir == 0 ? d0 : (dir == 1 ? d1 : d2);
-  const int o0 = dir == 0 ? no : d0, o1 = dir == 1 ? no : d1, o2 = dir == 2 ? no : d2;
-  const int total = o0 * o1 * o2;
-  const int istride = dir == 0 ? d1 * d2 : (dir == 1 ? d2 : 1);
-  for (int t = tid; t < total; t += nthreads)
+  const long long nth = (long long)gridDim.x * blockDim.x;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += nth)
   {
-    const int a0 = t / (o1 * o2), a1 = (t / o2) % o1, a2 = t % o2;
-    const int o = dir == 0 ? a0 : (dir == 1 ? a1 : a2);
-    const int base = (dir == 0 ? 0 : a0 * d1 * d2) + (dir == 1 ? 0 : a1 * d2) + (dir == 2 ? 0 : a2);
-    double s = 0.0;
-    for (int i = 0; i < ni; ++i)
-      s = fma(T ? M[i * no + o] : M[o * ni + i], in[base + i * istride], s);
-    out[t] = s;
+    const long long pos = t / nf3;
+    const int j = (int)(t - pos * nf3);
+    atomicMin(&first[dm_f[(long long)cells[pos] * nf3 + j]], (int32_t)pos);
+  }
+}
+// ... becomes one writer bit per (list position, local fine dof)
+__global__ void k_writer_mask(const int32_t* __restrict__ dm_f, const int32_t* __restrict__ cells,
+                              const int32_t* __restrict__ first, int nf3, int words, long long n_list,
+                              uint32_t* __restrict__ mask)
+{
+  const long long total = n_list * words;
+  const long long nth = (long long)gridDim.x * blockDim.x;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += nth)
+  {
+    const long long pos = t / words;
+    const int w = (int)(t - pos * words);
+    uint32_t bits = 0;
+    for (int b = 0; b < 32 && w * 32 + b < nf3; ++b)
+      if (first[dm_f[(long long)cells[pos] * nf3 + w * 32 + b]] == (int32_t)pos)
+        bits |= 1u << b;
+    mask[t] = bits;
   }
 }
 
-// One warp per cell (grid-stride over the cell list): the three 1-D passes run warp-synchronously
-// on a private shared-memory slice, so there is no block barrier and a CTA keeps several cells
-// in flight.  Prolongation: fine[dofs_f[j]] = sum_k M[j,k] coarse[dofs_c[k]] (overwrite; :21-45)
-__global__ void __launch_bounds__(IT)
-k_prolong(int nc, int nf, const double* __restrict__ M1, const int32_t* __restrict__ cells,
-          int first, int count, const int32_t* __restrict__ dm_c, const int32_t* __restrict__ dm_f,
-          const double* __restrict__ xc, double* __restrict__ xf)
+// Prolongation: fine[dofs_f[j]] (=|+=) sum_k M[j,k] coarse[dofs_c[k]]   (src/interpolate.hpp:21-45;
+// ADD folds the u += du of src/pmg.hpp:129, owned dofs only).
+template <int NC, int NF, bool ADD>
+__global__ void __launch_bounds__(XferCfg<NC, NF>::tpb)
+k_prolong(const __grid_constant__ InterpTab tab, const int32_t* __restrict__ cells, int first, int count,
+          const int32_t* __restrict__ dm_c, const int32_t* __restrict__ dm_f,
+          const uint32_t* __restrict__ wmask, const double* __restrict__ xc, double* __restrict__ xf,
+          int n_owned_f)
 {
-  extern __shared__ double sm[];
-  const int nc3 = nc * nc * nc, nf3 = nf * nf * nf;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  double* sM = sm;                            // nf*nc
-  double* b0 = sM + nf * nc + warp * 2 * nf3; // nf3 per warp
-  double* b1 = b0 + nf3;
-  for (int t = threadIdx.x; t < nf * nc; t += blockDim.x)
-    sM[t] = M1[t];
-  __syncthreads();
-  for (long long ci = (long long)blockIdx.x * wpb + warp; ci < count; ci += (long long)gridDim.x * wpb)
+  constexpr int TPB = XferCfg<NC, NF>::tpb, CPB = XferCfg<NC, NF>::cpb;
+  constexpr int NC3 = NC * NC * NC, NF3 = NF * NF * NF, W = (NF3 + 31) / 32;
+  __shared__ int32_t s_c[CPB * NC3];
+  __shared__ int32_t s_f[CPB * NF3]; // ~d when this cell is not the writer of d
+  const int tid = threadIdx.x;
+  const int cell0 = blockIdx.x * CPB;
+  for (int idx = tid; idx < CPB * NC3; idx += TPB)
   {
-    const long long cell = cells[first + ci];
-    for (int t = lane; t < nc3; t += 32)
-      b0[t] = xc[dm_c[cell * nc3 + t]];
-    __syncwarp();
-    contract_axis<false>(b0, b1, sM, nc, nc, nc, 2, nf, lane, 32); // [nc][nc][nf]
-    __syncwarp();
-    contract_axis<false>(b1, b0, sM, nc, nc, nf, 1, nf, lane, 32); // [nc][nf][nf]
-    __syncwarp();
-    contract_axis<false>(b0, b1, sM, nc, nf, nf, 0, nf, lane, 32); // [nf][nf][nf]
-    __syncwarp();
-    for (int t = lane; t < nf3; t += 32)
-      xf[dm_f[cell * nf3 + t]] = b1[t];
-    __syncwarp();
+    const int c = idx / NC3, j = idx - c * NC3;
+    s_c[idx] = cell0 + c < count ? dm_c[(long long)cells[first + cell0 + c] * NC3 + j] : 0;
   }
-}
-
-// Restriction: coarse[dofs_c[j]] += sum_k M[k,j] fine[d_k] / mult[d_k] (atomics; :60-87)
-__global__ void __launch_bounds__(IT)
-k_restrict(int nc, int nf, const double* __restrict__ M1, const int32_t* __restrict__ cells,
-           int first, int count, const int32_t* __restrict__ dm_c, const int32_t* __restrict__ dm_f,
-           const double* __restrict__ xf, const double* __restrict__ inv_mult, double* __restrict__ xc)
-{
-  extern __shared__ double sm[];
-  const int nc3 = nc * nc * nc, nf3 = nf * nf * nf;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  double* sM = sm;
-  double* b0 = sM + nf * nc + warp * 2 * nf3;
-  double* b1 = b0 + nf3;
-  for (int t = threadIdx.x; t < nf * nc; t += blockDim.x)
-    sM[t] = M1[t];
-  __syncthreads();
-  for (long long ci = (long long)blockIdx.x * wpb + warp; ci < count; ci += (long long)gridDim.x * wpb)
+  for (int idx = tid; idx < CPB * NF3; idx += TPB)
   {
-    const long long cell = cells[first + ci];
-    for (int t = lane; t < nf3; t += 32)
+    const int c = idx / NF3, j = idx - c * NF3;
+    int32_t d = 0;
+    if (cell0 + c < count)
     {
-      const int32_t d = dm_f[cell * nf3 + t];
-      b0[t] = xf[d] * inv_mult[d];
+      d = dm_f[(long long)cells[first + cell0 + c] * NF3 + j];
+      const uint32_t bits = wmask[(long long)(first + cell0 + c) * W + (j >> 5)];
+      if (!((bits >> (j & 31)) & 1u))
+        d = ~d;
     }
-    __syncwarp();
-    contract_axis<true>(b0, b1, sM, nf, nf, nf, 0, nc, lane, 32); // [nc][nf][nf]
-    __syncwarp();
-    contract_axis<true>(b1, b0, sM, nc, nf, nf, 1, nc, lane, 32); // [nc][nc][nf]
-    __syncwarp();
-    contract_axis<true>(b0, b1, sM, nc, nc, nf, 2, nc, lane, 32); // [nc][nc][nc]
-    __syncwarp();
-    for (int t = lane; t < nc3; t += 32)
-      atomicAdd(&xc[dm_c[cell * nc3 + t]], b1[t]);
-    __syncwarp();
+    s_f[idx] = d;
+  }
+  __syncthreads();
+  const int c = tid / NF, k = tid - c * NF;
+  if (c >= CPB || cell0 + c >= count)
+    return;
+  double mk[NC];
+#pragma unroll
+  for (int cz = 0; cz < NC; ++cz)
+    mk[cz] = tab.m[k * NC + cz];
+  // z pass: v[ix][iy] = sum_cz M[k][cz] xc[ix][iy][cz]
+  double v[NC][NC];
+  const int32_t* sc = s_c + c * NC3;
+#pragma unroll
+  for (int ix = 0; ix < NC; ++ix)
+#pragma unroll
+    for (int iy = 0; iy < NC; ++iy)
+    {
+      double s = 0.0;
+#pragma unroll
+      for (int cz = 0; cz < NC; ++cz)
+        s = fma(mk[cz], xc[sc[(ix * NC + iy) * NC + cz]], s);
+      v[ix][iy] = s;
+    }
+  // y pass: w[ix][fy] = sum_iy M[fy][iy] v[ix][iy]
+  double w[NC][NF];
+#pragma unroll
+  for (int ix = 0; ix < NC; ++ix)
+#pragma unroll
+    for (int fy = 0; fy < NF; ++fy)
+    {
+      double s = 0.0;
+#pragma unroll
+      for (int iy = 0; iy < NC; ++iy)
+        s = fma(tab.m[fy * NC + iy], v[ix][iy], s);
+      w[ix][fy] = s;
+    }
+  // x pass + store by the unique writer
+  const int32_t* sf = s_f + c * NF3 + k;
+#pragma unroll
+  for (int fx = 0; fx < NF; ++fx)
+#pragma unroll
+    for (int fy = 0; fy < NF; ++fy)
+    {
+      double s = 0.0;
+#pragma unroll
+      for (int ix = 0; ix < NC; ++ix)
+        s = fma(tab.m[fx * NC + ix], w[ix][fy], s);
+      const int32_t d = sf[(fx * NF + fy) * NF];
+      if (d >= 0)
+      {
+        if (ADD)
+        {
+          if (d < n_owned_f)
+            xf[d] = s * 1.0 + xf[d];
+        }
+        else
+          xf[d] = s;
+      }
+    }
+}
+
+// Restriction: coarse[dofs_c[j]] += sum_k M[k,j] (fine[d_k] - sub[d_k]) / mult[d_k]
+// (atomics; src/interpolate.hpp:60-87).  sub (may be null) is subtracted on owned fine dofs only:
+// it folds the smoother's last r -= q into the gather.
+template <int NC, int NF>
+__global__ void __launch_bounds__(XferCfg<NC, NF>::tpb)
+k_restrict(const __grid_constant__ InterpTab tab, const int32_t* __restrict__ cells, int first, int count,
+           const int32_t* __restrict__ dm_c, const int32_t* __restrict__ dm_f, const double* __restrict__ xf,
+           const double* __restrict__ sub, int n_owned_f, const double* __restrict__ inv_mult,
+           double* __restrict__ xc)
+{
+  constexpr int TPB = XferCfg<NC, NF>::tpb, CPB = XferCfg<NC, NF>::cpb;
+  constexpr int NC2 = NC * NC, NC3 = NC2 * NC, NF3 = NF * NF * NF;
+  __shared__ int32_t s_c[CPB * NC3];
+  __shared__ int32_t s_f[CPB * NF3];
+  __shared__ double s_v[CPB * NF * NC2];
+  const int tid = threadIdx.x;
+  const int cell0 = blockIdx.x * CPB;
+  for (int idx = tid; idx < CPB * NC3; idx += TPB)
+  {
+    const int c = idx / NC3, j = idx - c * NC3;
+    s_c[idx] = cell0 + c < count ? dm_c[(long long)cells[first + cell0 + c] * NC3 + j] : 0;
+  }
+  for (int idx = tid; idx < CPB * NF3; idx += TPB)
+  {
+    const int c = idx / NF3, j = idx - c * NF3;
+    s_f[idx] = cell0 + c < count ? dm_f[(long long)cells[first + cell0 + c] * NF3 + j] : 0;
+  }
+  __syncthreads();
+  const int c = tid / NF, k = tid - c * NF;
+  if (c < CPB)
+  {
+    const bool active = cell0 + c < count;
+    // transposed x pass: w[ix][fy] = sum_fx M[fx][ix] val[fx][fy]
+    double w[NC][NF];
+#pragma unroll
+    for (int ix = 0; ix < NC; ++ix)
+#pragma unroll
+      for (int fy = 0; fy < NF; ++fy)
+        w[ix][fy] = 0.0;
+    const int32_t* sf = s_f + c * NF3 + k;
+    if (active)
+    {
+#pragma unroll
+      for (int fx = 0; fx < NF; ++fx)
+#pragma unroll
+        for (int fy = 0; fy < NF; ++fy)
+        {
+          const int32_t d = sf[(fx * NF + fy) * NF];
+          double val = xf[d];
+          if (sub != nullptr && d < n_owned_f)
+            val = sub[d] * (-1.0) + val;
+          val *= inv_mult[d]; // src/interpolate.hpp:82
+#pragma unroll
+          for (int ix = 0; ix < NC; ++ix)
+            w[ix][fy] = fma(tab.m[fx * NC + ix], val, w[ix][fy]);
+        }
+    }
+    // transposed y pass: v[ix][iy] = sum_fy M[fy][iy] w[ix][fy]; handed to the z pass through smem
+    double* sv = s_v + (c * NF + k) * NC2;
+#pragma unroll
+    for (int ix = 0; ix < NC; ++ix)
+#pragma unroll
+      for (int iy = 0; iy < NC; ++iy)
+      {
+        double s = 0.0;
+#pragma unroll
+        for (int fy = 0; fy < NF; ++fy)
+          s = fma(tab.m[fy * NC + iy], w[ix][fy], s);
+        sv[ix * NC + iy] = s;
+      }
+  }
+  __syncthreads();
+  // transposed z pass: coarse (ix,iy,cz) += sum_k M[k][cz] v_k[ix][iy]; one atomic per coarse dof and cell
+  for (int idx = tid; idx < CPB * NC3; idx += TPB)
+  {
+    const int cc = idx / NC3, j = idx - cc * NC3;
+    if (cell0 + cc >= count)
+      break;
+    const int ixy = j / NC, cz = j - ixy * NC;
+    double s = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < NF; ++kk)
+      s = fma(tab.m[kk * NC + cz], s_v[(cc * NF + kk) * NC2 + ixy], s);
+    atomicAdd(&xc[s_c[idx]], s);
   }
 }
+
+// x[idx] - sub[idx] into the send buffer is done by the halo (halo_fwd_begin with sub)
 } // namespace
 } // namespace pmgx
 
@@ -134,26 +279,115 @@ struct pmgx_interp
   pmgx_halo* halo_c = nullptr;
   pmgx_halo* halo_f = nullptr;
   pmgx::DevBuf<int32_t> cells;   // lcells then bcells
-  pmgx::DevBuf<double> M1;       // [nf][nc]
+  pmgx::DevBuf<uint32_t> wmask;  // [n_list][ceil(nf^3/32)] unique-writer bits
   pmgx::DevBuf<double> inv_mult; // 1 / multiplicity of fine dofs
-  // warps per block: as many as fit ~40 KB of private slices (2 nf^3 doubles each), at most 8
-  int wpb() const
-  {
-    const int nf = pf + 1;
-    return std::max(1, std::min(8, (int)(40960 / (2 * nf * nf * nf * sizeof(double)))));
-  }
-  int tpb() const { return 32 * wpb(); }
-  size_t smem() const
-  {
-    const int nc = pc + 1, nf = pf + 1;
-    return (size_t)(nf * nc + wpb() * 2 * nf * nf * nf) * sizeof(double);
-  }
-  int grid(int count) const
-  {
-    const int blocks = (count + wpb() - 1) / wpb();
-    return std::max(1, std::min(blocks, ctx->num_sms * 16));
-  }
+  pmgx::InterpTab tab;
 };
+
+namespace pmgx
+{
+namespace
+{
+template <int NC, int NF>
+void launch_prolong(pmgx_interp* it, int first, int count, const double* xc, double* xf, bool add)
+{
+  if (count <= 0)
+    return;
+  pmgx_ctx* c = it->ctx;
+  using C = XferCfg<NC, NF>;
+  const int grid = (count + C::cpb - 1) / C::cpb;
+  const int n_owned_f = it->halo_f ? it->halo_f->n_owned : it->n_fine_total;
+  if (add)
+    k_prolong<NC, NF, true><<<grid, C::tpb, 0, c->stream>>>(it->tab, it->cells.p, first, count, it->dm_c, it->dm_f,
+                                                           it->wmask.p, xc, xf, n_owned_f);
+  else
+    k_prolong<NC, NF, false><<<grid, C::tpb, 0, c->stream>>>(it->tab, it->cells.p, first, count, it->dm_c, it->dm_f,
+                                                            it->wmask.p, xc, xf, n_owned_f);
+  check_launch("k_prolong");
+  count_launch(c);
+}
+
+template <int NC, int NF>
+void launch_restrict(pmgx_interp* it, int first, int count, const double* xf, const double* sub, double* xc)
+{
+  if (count <= 0)
+    return;
+  pmgx_ctx* c = it->ctx;
+  using C = XferCfg<NC, NF>;
+  const int grid = (count + C::cpb - 1) / C::cpb;
+  const int n_owned_f = it->halo_f ? it->halo_f->n_owned : it->n_fine_total;
+  k_restrict<NC, NF><<<grid, C::tpb, 0, c->stream>>>(it->tab, it->cells.p, first, count, it->dm_c, it->dm_f, xf, sub,
+                                                     n_owned_f, it->inv_mult.p, xc);
+  check_launch("k_restrict");
+  count_launch(c);
+}
+
+// dispatch on (coarse, fine) nodes per direction; pc <= pf
+template <int NF, typename F>
+void dispatch_nc(int nc, F&& f)
+{
+  switch (nc)
+  {
+  case 2: f(std::integral_constant<int, 2>{}); break;
+  case 3: if constexpr (NF >= 3) f(std::integral_constant<int, 3>{}); break;
+  case 4: if constexpr (NF >= 4) f(std::integral_constant<int, 4>{}); break;
+  case 5: if constexpr (NF >= 5) f(std::integral_constant<int, 5>{}); break;
+  case 6: if constexpr (NF >= 6) f(std::integral_constant<int, 6>{}); break;
+  case 7: if constexpr (NF >= 7) f(std::integral_constant<int, 7>{}); break;
+  case 8: if constexpr (NF >= 8) f(std::integral_constant<int, 8>{}); break;
+  case 9: if constexpr (NF >= 9) f(std::integral_constant<int, 9>{}); break;
+  default: break;
+  }
+}
+template <typename F>
+void dispatch(int nc, int nf, F&& f)
+{
+  switch (nf)
+  {
+  case 2: dispatch_nc<2>(nc, [&](auto NC) { f(NC, std::integral_constant<int, 2>{}); }); break;
+  case 3: dispatch_nc<3>(nc, [&](auto NC) { f(NC, std::integral_constant<int, 3>{}); }); break;
+  case 4: dispatch_nc<4>(nc, [&](auto NC) { f(NC, std::integral_constant<int, 4>{}); }); break;
+  case 5: dispatch_nc<5>(nc, [&](auto NC) { f(NC, std::integral_constant<int, 5>{}); }); break;
+  case 6: dispatch_nc<6>(nc, [&](auto NC) { f(NC, std::integral_constant<int, 6>{}); }); break;
+  case 7: dispatch_nc<7>(nc, [&](auto NC) { f(NC, std::integral_constant<int, 7>{}); }); break;
+  case 8: dispatch_nc<8>(nc, [&](auto NC) { f(NC, std::integral_constant<int, 8>{}); }); break;
+  case 9: dispatch_nc<9>(nc, [&](auto NC) { f(NC, std::integral_constant<int, 9>{}); }); break;
+  default: break;
+  }
+}
+} // namespace
+
+// interpolate (src/interpolate.hpp:185-239); add: fine += P coarse on owned fine dofs
+void interp_prolong(pmgx_interp* it, double* coarse, double* fine, bool add)
+{
+  pmgx_ctx* c = it->ctx;
+  PMGX_CUDA(cudaSetDevice(c->device));
+  if (it->halo_c)
+    halo_fwd_begin(it->halo_c, coarse);                                              // :202
+  dispatch(it->pc + 1, it->pf + 1, [&](auto NC, auto NF)
+           { launch_prolong<NC(), NF()>(it, 0, it->n_l, coarse, fine, add); });        // :208
+  if (it->halo_c)
+    halo_fwd_end(it->halo_c, coarse);                                                // :217
+  dispatch(it->pc + 1, it->pf + 1, [&](auto NC, auto NF)
+           { launch_prolong<NC(), NF()>(it, it->n_l, it->n_b, coarse, fine, add); });  // :227
+}
+
+// reverse_interpolate (src/interpolate.hpp:245-303) of fine - sub (sub may be null)
+void interp_restrict(pmgx_interp* it, double* fine, const double* sub, double* coarse)
+{
+  pmgx_ctx* c = it->ctx;
+  PMGX_CUDA(cudaSetDevice(c->device));
+  if (it->halo_f)
+    halo_fwd_begin(it->halo_f, fine, sub);                                           // :264
+  PMGX_CUDA(cudaMemsetAsync(coarse, 0, (size_t)it->n_coarse_total * sizeof(double), c->stream)); // :270
+  dispatch(it->pc + 1, it->pf + 1, [&](auto NC, auto NF)
+           { launch_restrict<NC(), NF()>(it, 0, it->n_l, fine, sub, coarse); });
+  if (it->halo_f)
+    halo_fwd_end(it->halo_f, fine);                                                  // :281
+  dispatch(it->pc + 1, it->pf + 1, [&](auto NC, auto NF)
+           { launch_restrict<NC(), NF()>(it, it->n_l, it->n_b, fine, sub, coarse); });
+}
+} // namespace pmgx
 
 extern "C"
 {
@@ -170,6 +404,10 @@ int pmgx_interp_create(pmgx_ctx* ctx, int degree_coarse, int degree_fine, int n_
   PMGX_REQUIRE(n_cells >= 0 && n_lcells >= 0 && n_bcells >= 0 && n_lcells + n_bcells <= n_cells,
                "interp_create: inconsistent cell counts");
   PMGX_REQUIRE(n_cells == 0 || (dofmap_coarse && dofmap_fine), "interp_create: null dofmap");
+  PMGX_REQUIRE(!halo_f || halo_f->n_owned + halo_f->n_ghost == n_fine_total,
+               "interp_create: fine halo does not match the fine vector layout");
+  PMGX_REQUIRE(!halo_c || halo_c->n_owned + halo_c->n_ghost == n_coarse_total,
+               "interp_create: coarse halo does not match the coarse vector layout");
   PMGX_CUDA(cudaSetDevice(ctx->device));
   std::unique_ptr<pmgx_interp> it(new pmgx_interp());
   it->ctx = ctx;
@@ -184,7 +422,8 @@ int pmgx_interp_create(pmgx_ctx* ctx, int degree_coarse, int degree_fine, int n_
   it->dm_f = dofmap_fine;
   it->halo_c = halo_c;
   it->halo_f = halo_f;
-  std::vector<int32_t> cl((size_t)n_lcells + n_bcells);
+  const int n_list = n_lcells + n_bcells;
+  std::vector<int32_t> cl((size_t)n_list);
   for (int i = 0; i < n_lcells; ++i)
     cl[i] = lcells_h[i];
   for (int i = 0; i < n_bcells; ++i)
@@ -194,26 +433,43 @@ int pmgx_interp_create(pmgx_ctx* ctx, int degree_coarse, int degree_fine, int n_
   it->cells.upload(cl.data(), cl.size(), ctx->stream);
   std::vector<double> M;
   pmgx::gll_interp_matrix(degree_coarse, degree_fine, M);
-  for (double& v : M) // the reference drops |v| <= 1e-12 when compressing (interpolate.hpp:120-128)
-    if (std::fabs(v) <= 1e-12)
-      v = 0.0;
-  it->M1.upload(M.data(), M.size(), ctx->stream);
+  std::memset(&it->tab, 0, sizeof(it->tab));
+  for (size_t i = 0; i < M.size(); ++i) // the reference drops |v| <= 1e-12 when compressing (interpolate.hpp:120-128)
+    it->tab.m[i] = std::fabs(M[i]) <= 1e-12 ? 0.0 : M[i];
+  const int nf = degree_fine + 1, nf3 = nf * nf * nf;
+  auto sgrid = [&](long long total)
+  { return (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, ctx->num_sms * 32)); };
   // multiplicity over the whole fine dofmap (all local + ghost cells, :172-178)
   it->inv_mult.alloc((size_t)n_fine_total);
   if (n_fine_total > 0)
   {
     PMGX_CUDA(cudaMemsetAsync(it->inv_mult.p, 0, (size_t)n_fine_total * sizeof(double), ctx->stream));
-    const int nf = degree_fine + 1;
-    const long long total = (long long)n_cells * nf * nf * nf;
+    const long long total = (long long)n_cells * nf3;
     if (total > 0)
     {
-      const int g = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, ctx->num_sms * 32));
-      pmgx::k_count_mult<<<g, 256, 0, ctx->stream>>>(dofmap_fine, total, it->inv_mult.p);
+      pmgx::k_count_mult<<<sgrid(total), 256, 0, ctx->stream>>>(dofmap_fine, total, it->inv_mult.p);
       pmgx::check_launch("k_count_mult");
     }
     pmgx::k_invert_mult<<<(n_fine_total + 255) / 256, 256, 0, ctx->stream>>>(it->inv_mult.p, n_fine_total);
     pmgx::check_launch("k_invert_mult");
     pmgx::count_launch(ctx, 2);
+  }
+  // unique writer of every fine dof: the first cell of the launch list that touches it
+  const int words = (nf3 + 31) / 32;
+  it->wmask.alloc((size_t)std::max(1, n_list) * words);
+  if (n_list > 0 && n_fine_total > 0)
+  {
+    pmgx::DevBuf<int32_t> first;
+    first.alloc((size_t)n_fine_total);
+    PMGX_CUDA(cudaMemsetAsync(first.p, 0x7f, (size_t)n_fine_total * sizeof(int32_t), ctx->stream));
+    const long long total = (long long)n_list * nf3;
+    pmgx::k_first_toucher<<<sgrid(total), 256, 0, ctx->stream>>>(dofmap_fine, it->cells.p, nf3, total, first.p);
+    pmgx::check_launch("k_first_toucher");
+    pmgx::k_writer_mask<<<sgrid((long long)n_list * words), 256, 0, ctx->stream>>>(
+        dofmap_fine, it->cells.p, first.p, nf3, words, n_list, it->wmask.p);
+    pmgx::check_launch("k_writer_mask");
+    pmgx::count_launch(ctx, 2);
+    PMGX_CUDA(cudaStreamSynchronize(ctx->stream));
   }
   PMGX_CUDA(cudaStreamSynchronize(ctx->stream));
   *out = it.release();
@@ -224,27 +480,7 @@ int pmgx_interp_prolong(pmgx_interp* it, double* coarse, double* fine)
 {
   PMGX_API_BEGIN
   PMGX_REQUIRE(it && coarse && fine, "interp_prolong: null argument");
-  pmgx_ctx* c = it->ctx;
-  PMGX_CUDA(cudaSetDevice(c->device));
-  const int nc = it->pc + 1, nf = it->pf + 1;
-  if (it->halo_c)
-    pmgx::halo_fwd_begin(it->halo_c, coarse);                                        // :202
-  if (it->n_l > 0)
-  {
-    pmgx::k_prolong<<<it->grid(it->n_l), it->tpb(), it->smem(), c->stream>>>(
-        nc, nf, it->M1.p, it->cells.p, 0, it->n_l, it->dm_c, it->dm_f, coarse, fine); // :208
-    pmgx::check_launch("k_prolong");
-    pmgx::count_launch(c);
-  }
-  if (it->halo_c)
-    pmgx::halo_fwd_end(it->halo_c, coarse);                                          // :217
-  if (it->n_b > 0)
-  {
-    pmgx::k_prolong<<<it->grid(it->n_b), it->tpb(), it->smem(), c->stream>>>(
-        nc, nf, it->M1.p, it->cells.p, it->n_l, it->n_b, it->dm_c, it->dm_f, coarse, fine); // :227
-    pmgx::check_launch("k_prolong");
-    pmgx::count_launch(c);
-  }
+  pmgx::interp_prolong(it, coarse, fine, false);
   PMGX_API_END
 }
 
@@ -252,28 +488,7 @@ int pmgx_interp_restrict(pmgx_interp* it, double* fine, double* coarse)
 {
   PMGX_API_BEGIN
   PMGX_REQUIRE(it && coarse && fine, "interp_restrict: null argument");
-  pmgx_ctx* c = it->ctx;
-  PMGX_CUDA(cudaSetDevice(c->device));
-  const int nc = it->pc + 1, nf = it->pf + 1;
-  if (it->halo_f)
-    pmgx::halo_fwd_begin(it->halo_f, fine);                                          // :264
-  PMGX_CUDA(cudaMemsetAsync(coarse, 0, (size_t)it->n_coarse_total * sizeof(double), c->stream)); // :270
-  if (it->n_l > 0)
-  {
-    pmgx::k_restrict<<<it->grid(it->n_l), it->tpb(), it->smem(), c->stream>>>(
-        nc, nf, it->M1.p, it->cells.p, 0, it->n_l, it->dm_c, it->dm_f, fine, it->inv_mult.p, coarse);
-    pmgx::check_launch("k_restrict");
-    pmgx::count_launch(c);
-  }
-  if (it->halo_f)
-    pmgx::halo_fwd_end(it->halo_f, fine);                                            // :281
-  if (it->n_b > 0)
-  {
-    pmgx::k_restrict<<<it->grid(it->n_b), it->tpb(), it->smem(), c->stream>>>(
-        nc, nf, it->M1.p, it->cells.p, it->n_l, it->n_b, it->dm_c, it->dm_f, fine, it->inv_mult.p, coarse);
-    pmgx::check_launch("k_restrict");
-    pmgx::count_launch(c);
-  }
+  pmgx::interp_restrict(it, fine, nullptr, coarse);
   PMGX_API_END
 }
 

@@ -20,7 +20,8 @@ struct pmgx_halo
 
 namespace pmgx
 {
-void halo_fwd_begin(pmgx_halo* h, double* x);
+// sub (may be null): the owners send x - sub instead of x (ghost block of x receives it)
+void halo_fwd_begin(pmgx_halo* h, double* x, const double* sub = nullptr);
 void halo_fwd_end(pmgx_halo* h, double* x);
 } // namespace pmgx
 
@@ -42,3 +43,12 @@ struct pmgx_operator
   // y = A x (zero fill + halo update of x included)
   virtual void apply(double* x, double* y) = 0;
 };
+
+struct pmgx_interp;
+namespace pmgx
+{
+// interpolate / reverse_interpolate (src/interpolate.hpp:185-303) with the fusions the V-cycle uses:
+// add: fine += P coarse on owned fine dofs; sub: restrict (fine - sub) with sub taken on owned dofs
+void interp_prolong(pmgx_interp* it, double* coarse, double* fine, bool add);
+void interp_restrict(pmgx_interp* it, double* fine, const double* sub, double* coarse);
+} // namespace pmgx

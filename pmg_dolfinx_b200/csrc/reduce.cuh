@@ -25,7 +25,7 @@ __device__ __forceinline__ double warp_max(double v)
 }
 
 // Reduce NV values per thread across the block, then across the grid: every block writes its
-// partial, the last block to finish (atomic ticket) sums the partials in block order, so the
+// partial, the last block to finish (atomic ticket) sums the partials in a fixed order, so the
 // result does not depend on scheduling.  out[k] receives value k.  Must be called by all
 // threads of a RED_THREADS-sized block.
 template <int NV, bool MAX = false>
@@ -65,20 +65,30 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], double* __restrict_
   if (!is_last)
     return;
   __threadfence();
+  // the last block sums the partials in a fixed (thread, warp) order with all of its threads
+#pragma unroll
+  for (int k = 0; k < NV; ++k)
+  {
+    double acc = MAX ? -1.0 : 0.0;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += RED_THREADS)
+    {
+      double pv = __ldcg(&partials[(size_t)b * NV + k]);
+      acc = MAX ? fmax(acc, pv) : acc + pv;
+    }
+    acc = MAX ? warp_max(acc) : warp_sum(acc);
+    if (lane == 0)
+      sh[k][warp] = acc;
+  }
+  __syncthreads();
   if (warp == 0)
   {
 #pragma unroll
     for (int k = 0; k < NV; ++k)
     {
-      double acc = MAX ? -1.0 : 0.0;
-      for (unsigned int b = lane; b < gridDim.x; b += 32)
-      {
-        double pv = __ldcg(&partials[(size_t)b * NV + k]);
-        acc = MAX ? fmax(acc, pv) : acc + pv;
-      }
-      acc = MAX ? warp_max(acc) : warp_sum(acc);
+      double w = lane < RED_THREADS / 32 ? sh[k][lane] : (MAX ? -1.0 : 0.0);
+      w = MAX ? warp_max(w) : warp_sum(w);
       if (lane == 0)
-        out[k] = acc;
+        out[k] = w;
     }
     if (lane == 0)
       *counter = 0u;

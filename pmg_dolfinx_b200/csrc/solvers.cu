@@ -80,6 +80,45 @@ k_cheb_step(const double* __restrict__ q, const double* __restrict__ dinv, doubl
   }
 }
 
+// Last iteration: only r -= q survives (the z update of chebyshev.hpp:80-83 is never read and
+// x is not touched after the last x += z at :73); optional ||r||^2.
+template <bool NORM>
+__global__ void __launch_bounds__(FT)
+k_cheb_last(const double* __restrict__ q, double* __restrict__ r, long long n, double* partials,
+            unsigned int* counter, double* out)
+{
+  const long long nth = (long long)gridDim.x * blockDim.x;
+  double s = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nth)
+  {
+    const double rv = q[i] * (-1.0) + r[i];
+    r[i] = rv;
+    if (NORM)
+      s = fma(rv, rv, s);
+  }
+  if (NORM)
+  {
+    double v[1] = {s};
+    grid_reduce<1>(v, partials, counter, out);
+  }
+}
+
+// x += z*c1 + c2*(D^-1 (r - q)): the step before a dropped last iteration -- r and z are dead
+template <int DUMMY>
+__global__ void __launch_bounds__(FT)
+k_cheb_step_xonly(const double* __restrict__ q, const double* __restrict__ dinv, const double* __restrict__ r,
+                  const double* __restrict__ z, double* __restrict__ x, double c1, double c2, long long n)
+{
+  const long long nth = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nth)
+  {
+    const double rv = q[i] * (-1.0) + r[i];
+    const double zs = z[i] * c1;
+    const double zv = (rv * dinv[i]) * c2 + zs;
+    x[i] = zv * 1.0 + x[i];
+  }
+}
+
 // r = b - y ; p = D^-1 r ; rnorm0 = p.r                               (cg.hpp:160-164)
 __global__ void __launch_bounds__(FT)
 k_cg_init(const double* __restrict__ b, const double* __restrict__ y, const double* __restrict__ dinv,
@@ -127,15 +166,75 @@ k_cg_update(double rnorm, const double* __restrict__ rnorm_dev, const double* __
   grid_reduce<1>(v, partials, counter, out);
 }
 
-// p = (rn_new / rn_old) p + y with the ratio formed on the device                (cg.hpp:197,211)
+// ---- single-reduction (Chronopoulos-Gear) PCG for the coarse solver: per iteration ONE vector
+// pass, ONE SpMV and ONE pass forming both inner products, so one all-reduce of 2 doubles.
+// r = b - q (q may be null: x = 0) ; u = D^-1 r ; optionally x = 0
 __global__ void __launch_bounds__(FT)
-k_cg_pupdate(const double* __restrict__ rn_new, const double* __restrict__ rn_old,
-             const double* __restrict__ y, double* __restrict__ p, long long n)
+k_cgcg_init(const double* __restrict__ b, const double* __restrict__ q, const double* __restrict__ dinv,
+            double* __restrict__ r, double* __restrict__ u, double* __restrict__ x, bool zero_x, long long n)
 {
-  const double beta = *rn_new / *rn_old;
   const long long nth = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nth)
-    p[i] = p[i] * beta + y[i];
+  {
+    const double rv = q ? q[i] * (-1.0) + b[i] : b[i];
+    r[i] = rv;
+    u[i] = rv * dinv[i];
+    if (zero_x)
+      x[i] = 0.0;
+  }
+}
+
+// sc_cur = {gamma = r.u, delta = w.u} of this iteration, sc_old[0] = previous gamma.
+//   beta = gamma/gamma_old, alpha = gamma / (delta - beta*gamma/alpha_old)   (first: beta = 0)
+//   p = u + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s ; u = D^-1 r
+__global__ void __launch_bounds__(FT)
+k_cgcg_update(const double* __restrict__ sc_cur, const double* __restrict__ sc_old,
+              const double* __restrict__ alpha_old, double* __restrict__ alpha_out,
+              double* __restrict__ gamma0_out, bool first,
+              const double* __restrict__ dinv, const double* __restrict__ w, double* __restrict__ p,
+              double* __restrict__ s, double* __restrict__ x, double* __restrict__ r, double* __restrict__ u,
+              long long n)
+{
+  const double gamma = sc_cur[0], delta = sc_cur[1];
+  double beta = first ? 0.0 : gamma / sc_old[0];
+  double alpha = first ? gamma / delta : gamma / (delta - beta * gamma / *alpha_old);
+  if (!(gamma > 0.0)) // r = 0: the iterate is exact, freeze it
+    alpha = 0.0, beta = 0.0;
+  const long long nth = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nth)
+  {
+    const double pv = first ? u[i] : fma(beta, p[i], u[i]);
+    const double sv = first ? w[i] : fma(beta, s[i], w[i]);
+    p[i] = pv;
+    s[i] = sv;
+    x[i] = fma(alpha, pv, x[i]);
+    const double rv = fma(-alpha, sv, r[i]);
+    r[i] = rv;
+    u[i] = rv * dinv[i];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+  {
+    *alpha_out = alpha;
+    if (first)
+      gamma0_out[0] = gamma; // r0.D^-1 r0 for the relative convergence test
+  }
+}
+
+// out[0] = r.u, out[1] = w.u
+__global__ void __launch_bounds__(FT)
+k_dot2(const double* __restrict__ r, const double* __restrict__ w, const double* __restrict__ u, long long n,
+       double* partials, unsigned int* counter, double* out)
+{
+  const long long nth = (long long)gridDim.x * blockDim.x;
+  double a = 0.0, b = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nth)
+  {
+    const double uv = u[i];
+    a = fma(r[i], uv, a);
+    b = fma(w[i], uv, b);
+  }
+  double v[2] = {a, b};
+  grid_reduce<2>(v, partials, counter, out);
 }
 
 void check(const char* w) { check_launch(w); }
@@ -155,14 +254,30 @@ struct pmgx_cheb
 namespace pmgx
 {
 // x <- Chebyshev(A, x, b). hist: max_iter+1 residual norms or nullptr.
+// final_r says what the caller needs of the recurrence residual r = b - A x_final afterwards:
+//   CHEB_R_NONE   nothing: the last iteration of the reference (one apply + one pass that only
+//                 feed r and a z nobody reads, chebyshev.hpp:76-83) is dropped; x is bit-identical
+//   CHEB_R_FULL   s->r holds r
+//   CHEB_R_SPLIT  s->r - s->q is r (the caller folds the subtraction into its own gather)
+enum ChebResidual
+{
+  CHEB_R_NONE = 0,
+  CHEB_R_FULL = 1,
+  CHEB_R_SPLIT = 2
+};
+
 void cheb_solve(pmgx_cheb* s, pmgx_operator* A, double* x, const double* b, double* hist,
-                bool x_is_zero = false)
+                bool x_is_zero = false, ChebResidual final_r = CHEB_R_FULL)
 {
   pmgx_ctx* c = s->ctx;
   const long long n = s->n_owned;
   const double lmax = s->eig_max; // only the upper bound is used (chebyshev.hpp:51)
   const double* dinv = A->diag_inv.p; // get_diag_inverse without the per-call copy (:53)
   const int grid = fused_grid(c, n);
+  if (hist)
+    final_r = CHEB_R_FULL; // every iteration's ||r|| is reported
+  if (s->max_iter == 0 && final_r == CHEB_R_SPLIT)
+    final_r = CHEB_R_FULL;
   if (!x_is_zero)
     A->apply(x, s->q.p); // :56
   const double* q0 = x_is_zero ? nullptr : s->q.p; // A*0 = 0: skip the apply, r = b
@@ -183,17 +298,41 @@ void cheb_solve(pmgx_cheb* s, pmgx_operator* A, double* x, const double* b, doub
   }
   for (int i = 1; i <= s->max_iter; ++i)
   {
+    const bool last = i == s->max_iter;
+    if (last && final_r == CHEB_R_NONE)
+      break; // nothing of this iteration is observable
     A->apply(s->z.p, s->q.p); // :76
+    if (last && final_r == CHEB_R_SPLIT)
+      break; // r = s->r - s->q, combined by the caller
     const double c1 = double(2 * i - 1) / double(2 * i + 3);
     const double c2 = double(8 * i + 4) / double(2 * i + 3) / lmax;
-    const bool add = i < s->max_iter; // the x += z of iteration i+1 (:73)
-    if (hist)
-      k_cheb_step<true><<<grid, FT, 0, c->stream>>>(s->q.p, dinv, s->r.p, s->z.p, x, c1, c2, add, n,
-                                                    c->d_partials, c->d_counter, c->d_scalars + 8);
+    if (last)
+    {
+      if (hist)
+        k_cheb_last<true><<<grid, FT, 0, c->stream>>>(s->q.p, s->r.p, n, c->d_partials, c->d_counter,
+                                                      c->d_scalars + 8);
+      else
+        k_cheb_last<false><<<grid, FT, 0, c->stream>>>(s->q.p, s->r.p, n, c->d_partials, c->d_counter,
+                                                       c->d_scalars + 8);
+      check("k_cheb_last");
+    }
+    else if (i + 1 == s->max_iter && final_r == CHEB_R_NONE)
+    {
+      // the next iteration is dropped, so r and z of this one are dead as well
+      k_cheb_step_xonly<0><<<grid, FT, 0, c->stream>>>(s->q.p, dinv, s->r.p, s->z.p, x, c1, c2, n);
+      check("k_cheb_step_xonly");
+    }
     else
-      k_cheb_step<false><<<grid, FT, 0, c->stream>>>(s->q.p, dinv, s->r.p, s->z.p, x, c1, c2, add, n,
-                                                     c->d_partials, c->d_counter, c->d_scalars + 8);
-    check("k_cheb_step");
+    {
+      // the x += z of iteration i+1 (:73) is folded into this pass
+      if (hist)
+        k_cheb_step<true><<<grid, FT, 0, c->stream>>>(s->q.p, dinv, s->r.p, s->z.p, x, c1, c2, true, n,
+                                                      c->d_partials, c->d_counter, c->d_scalars + 8);
+      else
+        k_cheb_step<false><<<grid, FT, 0, c->stream>>>(s->q.p, dinv, s->r.p, s->z.p, x, c1, c2, true, n,
+                                                       c->d_partials, c->d_counter, c->d_scalars + 8);
+      check("k_cheb_step");
+    }
     count_launch(c);
     if (hist)
     {
@@ -213,6 +352,7 @@ struct pmgx_cg
   double rtol = 0.0;
   bool store = false;
   pmgx::DevBuf<double> r, y, p; // src/cg.hpp:241-244
+  pmgx::DevBuf<double> u, s2;   // extra work vectors of the single-reduction coarse variant (lazy)
   std::vector<double> alphas, betas, residuals; // stored coefficients (:213-218)
   std::vector<double> history;                  // every iteration's r.M^-1 r
   double rnorm0 = 0.0;
@@ -273,50 +413,72 @@ int cg_solve(pmgx_cg* s, pmgx_operator* A, double* x, const double* b)
 
 namespace pmgx
 {
-// Same recurrence as cg_solve, but alpha and beta never leave the device: the host only looks
-// at the residual every `check_every` iterations, so an iteration costs launches and two
-// all-reduces, no host round trip.  Used by the coarse solver, where iteration counts are not a
-// parity quantity (the reference runs PETSc CG + BoomerAMG there, src/amg.hpp:33-47).
-int cg_solve_device(pmgx_cg* s, pmgx_operator* A, double* x, const double* b, int check_every)
+// Coarse-level PCG (Jacobi), single-reduction form: mathematically the CG of src/cg.hpp, but the
+// two inner products of an iteration are formed together in one pass, alpha/beta never leave
+// the device and the host only looks at r.D^-1 r every `check_every` iterations.  Iteration
+// counts of this inner solve are not a parity quantity (the reference runs PETSc CG + BoomerAMG
+// here, src/amg.hpp:33-47).  s->y doubles as w = A u; work vectors p, s2, u are the solver's.
+int cgcg_solve(pmgx_cg* s, pmgx_operator* A, double* x, const double* b, int check_every, bool x_is_zero)
 {
   pmgx_ctx* c = s->ctx;
   const long long n = s->n_owned;
   const double* dinv = A->diag_inv.p;
   const int grid = fused_grid(c, n);
-  double* rn = c->d_scalars + 16; // rn[0], rn[1]: ping-pong r.M^-1 r
-  double* pap = c->d_scalars + 18;
-  A->apply(x, s->y.p);
-  k_cg_init<<<grid, FT, 0, c->stream>>>(b, s->y.p, dinv, s->r.p, s->p.p, n, c->d_partials, c->d_counter, rn);
-  check("k_cg_init");
+  const size_t nt = (size_t)s->n_owned + s->n_ghost;
+  if (s->u.n != nt)
+  {
+    s->u.alloc(nt);
+    s->s2.alloc(nt);
+    if (nt > 0)
+    {
+      PMGX_CUDA(cudaMemsetAsync(s->u.p, 0, nt * sizeof(double), c->stream));
+      PMGX_CUDA(cudaMemsetAsync(s->s2.p, 0, nt * sizeof(double), c->stream));
+    }
+  }
+  double* sc = c->d_scalars + 16;  // sc[2*(it&1) + {0,1}] = {gamma, delta}
+  double* al = c->d_scalars + 20;  // al[it&1] = alpha
+  double* w = s->y.p;
+  auto spmv_dots = [&](double* out2, int slot)
+  {
+    A->apply(s->u.p, w);
+    k_dot2<<<grid, FT, 0, c->stream>>>(s->r.p, w, s->u.p, n, c->d_partials, c->d_counter, out2);
+    check("k_dot2");
+    count_launch(c);
+    vec::allreduce_scalars(c, slot, 2, false);
+  };
+  if (!x_is_zero)
+    A->apply(x, w);
+  k_cgcg_init<<<grid, FT, 0, c->stream>>>(b, x_is_zero ? nullptr : w, dinv, s->r.p, s->u.p, x, x_is_zero, n);
+  check("k_cgcg_init");
   count_launch(c);
-  vec::allreduce_scalars(c, 16, 1, false);
-  const double rnorm0 = vec::read_scalar(c, 16);
-  s->rnorm0 = rnorm0;
+  spmv_dots(sc, 16);
   s->history.clear();
-  if (!(rnorm0 > 0.0))
-    return 0;
   const double rtol2 = s->rtol * s->rtol;
+  double* g0 = c->d_scalars + 22; // gamma of iteration 0, next to the ping-pong slots: one D2H reads both
   int k = 0;
   while (k < s->max_iter)
   {
     const int cur = k & 1, nxt = cur ^ 1;
+    k_cgcg_update<<<grid, FT, 0, c->stream>>>(sc + 2 * cur, sc + 2 * nxt, al + nxt, al + cur, g0, k == 0, dinv, w,
+                                              s->p.p, s->s2.p, x, s->r.p, s->u.p, n);
+    check("k_cgcg_update");
+    count_launch(c);
     ++k;
-    A->apply(s->p.p, s->y.p);
-    vec::dot_device(c, s->p.p, s->y.p, n, 18);
-    k_cg_update<<<grid, FT, 0, c->stream>>>(0.0, rn + cur, pap, s->p.p, dinv, x, s->r.p, s->y.p, n,
-                                            c->d_partials, c->d_counter, rn + nxt);
-    check("k_cg_update");
-    vec::allreduce_scalars(c, 16 + nxt, 1, false);
-    if (k % check_every == 0 || k == s->max_iter)
+    if (k == s->max_iter)
+      break;
+    spmv_dots(sc + 2 * nxt, 16 + 2 * nxt);
+    if (k % check_every == 0)
     {
-      const double r = vec::read_scalar(c, 16 + nxt);
+      // the only host round trips of the solve: gamma slots 16..19, alpha 20..21, gamma0 22
+      PMGX_CUDA(cudaMemcpyAsync(c->h_scalars + 16, c->d_scalars + 16, 7 * sizeof(double), cudaMemcpyDeviceToHost,
+                                c->stream));
+      PMGX_CUDA(cudaStreamSynchronize(c->stream));
+      const double r = c->h_scalars[16 + 2 * nxt];
+      s->rnorm0 = c->h_scalars[22];
       s->history.push_back(r);
-      if (r / rnorm0 < rtol2)
+      if (!(r > 0.0) || r / s->rnorm0 < rtol2)
         break;
     }
-    k_cg_pupdate<<<grid, FT, 0, c->stream>>>(rn + nxt, rn + cur, s->y.p, s->p.p, n);
-    check("k_cg_pupdate");
-    count_launch(c, 2);
   }
   return k;
 }
@@ -341,27 +503,9 @@ struct pmgx_vcycle
   std::vector<pmgx_interp*> interps;
   std::vector<const int8_t*> bc;
   pmgx_coarse* coarse = nullptr;
-  std::vector<pmgx::DevBuf<double>> u, r, b, du; // src/pmg.hpp:165-168
+  std::vector<pmgx::DevBuf<double>> u, r, b; // src/pmg.hpp:165-168 (du folded into the prolongation)
   std::vector<double> diagnostics;
 };
-
-namespace pmgx
-{
-namespace
-{
-// r = b - A u on level i; optionally its norm
-double residual(pmgx_vcycle* v, int i, bool want_norm)
-{
-  pmgx_ctx* c = v->ctx;
-  pmgx_operator* A = v->ops[i];
-  A->apply(v->u[i].p, v->r[i].p);
-  vec::axpy(c, v->r[i].p, -1.0, v->r[i].p, v->b[i].p, A->n_owned);
-  if (!want_norm)
-    return 0.0;
-  return std::sqrt(vec::dot(c, v->r[i].p, v->r[i].p, A->n_owned));
-}
-} // namespace
-} // namespace pmgx
 
 extern "C"
 {
@@ -404,7 +548,8 @@ int pmgx_cheb_solve(pmgx_cheb* s, pmgx_operator* A, double* x, const double* b, 
   PMGX_REQUIRE(s && A && x && b, "cheb_solve: null argument");
   PMGX_REQUIRE(A->n_owned == s->n_owned && A->n_ghost == s->n_ghost, "Incompatible vector sizes");
   PMGX_CUDA(cudaSetDevice(s->ctx->device));
-  pmgx::cheb_solve(s, A, x, b, resid_hist_h);
+  // the recurrence residual is private to the solver: drop the reference's dead last iteration
+  pmgx::cheb_solve(s, A, x, b, resid_hist_h, false, pmgx::CHEB_R_NONE);
   PMGX_API_END
 }
 int pmgx_cheb_residual(pmgx_cheb* s, pmgx_operator* A, double* x, const double* b, double* rnorm_h)
@@ -578,7 +723,7 @@ int pmgx_coarse_solve(pmgx_coarse* cs, double* x, const double* b, int* iters_h)
   PMGX_API_BEGIN
   PMGX_REQUIRE(cs && x && b, "coarse_solve: null argument");
   PMGX_CUDA(cudaSetDevice(cs->ctx->device));
-  const int k = pmgx::cg_solve_device(cs->cg, cs->A, x, b, 8);
+  const int k = pmgx::cgcg_solve(cs->cg, cs->A, x, b, 8, false);
   if (iters_h)
     *iters_h = k;
   PMGX_API_END
@@ -611,7 +756,6 @@ int pmgx_vcycle_create(pmgx_ctx* ctx, int n_levels, pmgx_operator** ops, pmgx_ch
   v->u.resize(n_levels);
   v->r.resize(n_levels);
   v->b.resize(n_levels);
-  v->du.resize(n_levels);
   for (int i = 0; i < n_levels; ++i)
   {
     PMGX_REQUIRE(ops[i] && smoothers[i] && bc_markers[i], "vcycle_create: null level %d", i);
@@ -625,8 +769,11 @@ int pmgx_vcycle_create(pmgx_ctx* ctx, int n_levels, pmgx_operator** ops, pmgx_ch
       v->interps.push_back(interps[i]);
     }
     const size_t nt = (size_t)ops[i]->n_owned + ops[i]->n_ghost;
-    for (auto* buf : {&v->u[i], &v->r[i], &v->b[i], &v->du[i]})
+    const bool is_top = i == n_levels - 1 && n_levels > 1;
+    for (auto* buf : {&v->u[i], &v->r[i], &v->b[i]})
     {
+      if (is_top && buf != &v->r[i])
+        continue; // the cycle works on the caller's top-level u and b in place
       buf->alloc(nt);
       if (nt > 0)
         PMGX_CUDA(cudaMemsetAsync(buf->p, 0, nt * sizeof(double), ctx->stream));
@@ -649,71 +796,94 @@ int pmgx_vcycle_apply(pmgx_vcycle* v, const double* b_in, double* u_inout, doubl
   const bool literal_seq = (v->flags & PMGX_VC_LITERAL_SEQUENCE) != 0;
   v->diagnostics.clear();
   namespace vec = pmgx::vec;
+  // The reference copies x into _b[top] and y into _u[top] and back (pmg.hpp:65-68,154); both
+  // are full owned+ghost vectors, so the cycle works on the caller's arrays directly.
+  std::vector<double*> U(nl);
+  std::vector<const double*> B(nl);
+  for (int i = 0; i < top; ++i)
+    U[i] = v->u[i].p, B[i] = v->b[i].p;
+  U[top] = u_inout;
+  B[top] = b_in;
+  auto residual = [&](int i, bool want_norm) -> double // r = b - A u on level i; optionally its norm
+  {
+    pmgx_operator* A = v->ops[i];
+    A->apply(U[i], v->r[i].p);
+    vec::axpy(c, v->r[i].p, -1.0, v->r[i].p, B[i], A->n_owned);
+    if (!want_norm)
+      return 0.0;
+    return std::sqrt(vec::dot(c, v->r[i].p, v->r[i].p, A->n_owned));
+  };
   for (int i = 0; i < top; ++i) // pmg.hpp:63-64
-    vec::set(c, v->u[i].p, (long long)v->ops[i]->n_owned + v->ops[i]->n_ghost, 0.0);
-  vec::copy(c, v->u[top].p, u_inout, v->ops[top]->n_owned); // :65
-  vec::copy(c, v->b[top].p, b_in, v->ops[top]->n_owned);    // :68
+    vec::set(c, U[i], (long long)v->ops[i]->n_owned + v->ops[i]->n_ghost, 0.0);
 
   for (int i = top; i > 0; --i)
   {
     if (diag)
-      v->diagnostics.push_back(pmgx::residual(v, i, true));                       // :76-80
-    // below the top level u is zero on the way down: the smoother's first apply is skipped
-    pmgx::cheb_solve(v->smoothers[i], v->ops[i], v->u[i].p, v->b[i].p, nullptr, !literal_seq && i < top); // :83
+      v->diagnostics.push_back(residual(i, true));                                // :76-80
+    // below the top level u is zero on the way down: the smoother's first apply is skipped.
+    // The smoother's recurrence already holds r = b - A u of its final iterate
+    // (src/chebyshev.hpp:73-77; the reference recomputes it with one more apply, :86-89), and
+    // the last r -= q is folded into the restriction's gather.
+    const pmgx::ChebResidual want = literal_seq ? pmgx::CHEB_R_FULL : (diag ? pmgx::CHEB_R_FULL : pmgx::CHEB_R_SPLIT);
+    pmgx::cheb_solve(v->smoothers[i], v->ops[i], U[i], B[i], nullptr, !literal_seq && i < top, want); // :83
     double* rfine = v->r[i].p;
+    const double* rsub = nullptr;
     if (literal_seq)
     {
-      const double rn = pmgx::residual(v, i, diag);                               // :86-89
+      const double rn = residual(i, diag);                                        // :86-89
       if (diag)
         v->diagnostics.push_back(rn);
     }
     else
     {
-      // the smoother's recurrence already holds r = b - A u of its final iterate
-      // (src/chebyshev.hpp:73-77); the reference recomputes it with one more apply
       rfine = v->smoothers[i]->r.p;
+      if (want == pmgx::CHEB_R_SPLIT && v->smoothers[i]->max_iter > 0)
+        rsub = v->smoothers[i]->q.p;
       if (diag)
         v->diagnostics.push_back(std::sqrt(vec::dot(c, rfine, rfine, v->ops[i]->n_owned)));
     }
-    int rc = pmgx_interp_restrict(v->interps[i - 1], rfine, v->b[i - 1].p);       // :92
-    if (rc != PMGX_OK)
-      return rc;
+    pmgx::interp_restrict(v->interps[i - 1], rfine, rsub, v->b[i - 1].p);          // :92
     if (!literal_bc && i - 1 > 0) // quirk Q9: keep Dirichlet rows of intermediate levels clean
       vec::mask_bc(c, v->b[i - 1].p, v->bc[i - 1], v->ops[i - 1]->n_owned);
   }
-  vec::mask_bc(c, v->b[0].p, v->bc[0], v->ops[0]->n_owned);                        // :100-103
+  if (nl > 1)
+    vec::mask_bc(c, v->b[0].p, v->bc[0], v->ops[0]->n_owned);                      // :100-103
+  else
+  {
+    // single level: the reference masks its private copy of b; keep the caller's b intact
+    vec::copy(c, v->b[0].p, b_in, v->ops[0]->n_owned);
+    vec::mask_bc(c, v->b[0].p, v->bc[0], v->ops[0]->n_owned);
+    B[0] = v->b[0].p;
+  }
+  const pmgx::ChebResidual post = literal_seq ? pmgx::CHEB_R_FULL : pmgx::CHEB_R_NONE;
   if (v->coarse && nl > 1)
   {
-    int rc = pmgx_coarse_solve(v->coarse, v->u[0].p, v->b[0].p, nullptr);         // :106-107
-    if (rc != PMGX_OK)
-      return rc;
+    pmgx::cgcg_solve(v->coarse->cg, v->coarse->A, U[0], B[0], 8, true);           // :106-107 (u[0] = 0)
   }
   else
-    pmgx::cheb_solve(v->smoothers[0], v->ops[0], v->u[0].p, v->b[0].p, nullptr, !literal_seq && nl > 1); // :109
+    pmgx::cheb_solve(v->smoothers[0], v->ops[0], U[0], B[0], nullptr, !literal_seq && nl > 1, post); // :109
   if (diag)
-    v->diagnostics.push_back(pmgx::residual(v, 0, true));                         // :114-117
+    v->diagnostics.push_back(residual(0, true));                                  // :114-117
 
   for (int i = 0; i < top; ++i)
   {
-    int rc = pmgx_interp_prolong(v->interps[i], v->u[i].p, v->du[i + 1].p);       // :123
-    if (rc != PMGX_OK)
-      return rc;
-    vec::axpy(c, v->u[i + 1].p, 1.0, v->u[i + 1].p, v->du[i + 1].p, v->ops[i + 1]->n_owned); // :129
+    // u[i+1] += P u[i]: the reference prolongs into du and adds (:123-129); the sum is formed in
+    // the prolongation's store
+    pmgx::interp_prolong(v->interps[i], U[i], U[i + 1], true);
     if (diag)
-      v->diagnostics.push_back(pmgx::residual(v, i + 1, true));                   // :132-135
-    pmgx::cheb_solve(v->smoothers[i + 1], v->ops[i + 1], v->u[i + 1].p, v->b[i + 1].p, nullptr); // :138
+      v->diagnostics.push_back(residual(i + 1, true));                            // :132-135
+    pmgx::cheb_solve(v->smoothers[i + 1], v->ops[i + 1], U[i + 1], B[i + 1], nullptr, false, post); // :138
     if (diag && i + 1 < top)
-      v->diagnostics.push_back(pmgx::residual(v, i + 1, true));                   // :141-144
+      v->diagnostics.push_back(residual(i + 1, true));                            // :141-144
   }
   if (rnorm_h || diag)
   {
-    const double rn = pmgx::residual(v, top, true);                               // :141-149
+    const double rn = residual(top, true);                                        // :141-149
     if (rnorm_h)
       *rnorm_h = rn;
     if (diag)
       v->diagnostics.push_back(rn);
   }
-  vec::copy(c, u_inout, v->u[top].p, v->ops[top]->n_owned);                        // :154
   PMGX_API_END
 }
 

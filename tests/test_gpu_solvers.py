@@ -239,3 +239,40 @@ def test_vcycle_history(ctx, degrees, n, coarse):
         assert rel(u.data_copy(), uo)[0] < 1e-9
     if coarse:
         assert hov[-1] < 1e-2 * np.linalg.norm(b)
+
+
+@pytest.mark.parametrize("degrees,n,coarse", [((1, 3), (6, 6, 6), True), ((1, 2, 4), (4, 4, 4), False),
+                                                ((1, 2, 4), (4, 5, 3), True)])
+@pytest.mark.parametrize("flags", [0, 4])
+def test_vcycle_default_and_literal_sequence_match_oracle(ctx, degrees, n, coarse, flags):
+    """The production cycle (flags 0: the smoother's recurrence residual is restricted with the last
+    r -= q folded into the gather, u += P u_c is formed in the prolongation's store, the reference's
+    dead last smoothing iteration is dropped, the cycle works on the caller's vectors in place) and
+    the literal reference sequence (flags 4) give the oracle's iterates."""
+    from pmg_dolfinx_b200 import api
+    mesh = om.create_box(*n, perturb=0.1)
+    ols, gls, olev, smoothers, interps, pro, res = _build_hierarchy(ctx, mesh, degrees)
+    top = ols[-1]
+    b = oo.rhs_collocated(mesh, top.P, oo.f_sines(1, 2, 1, 2.0), top.bc)
+    cs_o, cs_g = None, None
+    if coarse:
+        A0 = oo.assemble_csr(ols[0].P, ols[0].dm, ols[0].G, ols[0].kappa, ols[0].bc, ols[0].nd)
+        d0 = 1.0 / A0.diagonal()
+        cs_o = lambda u0, b0: osol.cg(lambda v: A0 @ v, d0, u0, b0, 200, 1e-12)[0]
+        cs_g = api.CoarseSolverType(ctx, gls[0].op.to_csr(), 200, 1e-12)
+    pmg = api.MultigridPreconditioner(ctx, [g.bc for g in gls], flags=flags)
+    pmg.set_solvers(smoothers)
+    pmg.set_operators([g.op for g in gls])
+    pmg.set_interpolators(interps)
+    pmg.set_coarse_solver(cs_g)
+    u = gls[-1].vec()
+    bv = gls[-1].vec(b)
+    uo = np.zeros(top.nd)
+    b_before = bv.data_copy().copy()
+    for it in range(3):
+        ho = []
+        uo = osol.vcycle(olev, pro, res, b, uo, coarse_solve=cs_o, history=ho)
+        rn = pmg.apply(bv, u, verbose=True)
+        assert abs(rn - ho[-1][2]) <= 1e-9 * ho[0][2]
+        assert rel(u.data_copy(), uo)[0] < 1e-9
+    assert np.array_equal(bv.data_copy(), b_before)      # the caller's b is never modified
