@@ -82,6 +82,10 @@ long long pmgx_ctx_launch_count(pmgx_ctx* ctx);
 /* Per-kernel timing of the matrix-free apply kernel (bench roofline): while on, every launch of
  * the apply kernel is bracketed by CUDA events on the compute stream; _read synchronises and
  * returns the summed device time and the launch count for one degree, then clears them. */
+/* 1 when the NVLink peer-memory path is active (nranks > 1, all ranks on one node, CUDA IPC
+ * available, PMGX_P2P != 0): halo values and all-reduce operands are stored straight into the
+ * peers' memory by the library's own kernels; 0: grouped ncclSend/ncclRecv + ncclAllReduce. */
+int pmgx_ctx_uses_p2p(pmgx_ctx* ctx);
 int pmgx_ctx_profile(pmgx_ctx* ctx, int on);
 int pmgx_ctx_profile_read(pmgx_ctx* ctx, int degree, double* ms_total_h, long long* launches_h);
 
@@ -90,16 +94,21 @@ int pmgx_ctx_profile_read(pmgx_ctx* ctx, int degree, double* ms_total_h, long lo
  * acc::Vector, src/vector.hpp:83-95).  send_idx_h: owned local indices grouped by
  * destination rank (Scatterer::local_indices); recv_idx_h: ghost slot (0-based in
  * the ghost block) of each received value grouped by source rank
- * (Scatterer::remote_indices).  The index arrays are copied. */
+ * (Scatterer::remote_indices).  The index arrays are copied.  With nranks > 1 this call is
+ * COLLECTIVE (like constructing a Scatterer on an MPI communicator): every rank must create its
+ * halos in the same order, because the ranks exchange the IPC handles of their receive buffers. */
 int pmgx_halo_create(pmgx_ctx* ctx, int n_owned, int n_ghost,
                      int n_send_nbr, const int* send_ranks_h, const int* send_offsets_h,
                      const int32_t* send_idx_h,
                      int n_recv_nbr, const int* recv_ranks_h, const int* recv_offsets_h,
                      const int32_t* recv_idx_h, pmgx_halo** out);
 int pmgx_halo_destroy(pmgx_halo* h);
-/* Vector::scatter_fwd_begin / scatter_fwd_end (src/vector.hpp:186-238): pack kernel +
- * grouped ncclSend/ncclRecv on the comm stream, then unpack; the compute stream only
- * waits in _end. */
+int pmgx_halo_uses_p2p(pmgx_halo* h);
+/* Vector::scatter_fwd_begin / scatter_fwd_end (src/vector.hpp:186-238) on the comm stream:
+ * peer-memory path: ONE kernel packs and stores into the neighbours' receive buffers over NVLink
+ * and releases an epoch flag, a one-CTA kernel waits for the neighbours' flags, then unpack;
+ * NCCL path: pack kernel + grouped ncclSend/ncclRecv + unpack.  The compute stream only waits
+ * in _end. */
 int pmgx_halo_fwd_begin(pmgx_halo* h, double* x);
 int pmgx_halo_fwd_end(pmgx_halo* h, double* x);
 /* Vector::scatter_rev (src/vector.hpp:249-294): ghost -> owner accumulate. */

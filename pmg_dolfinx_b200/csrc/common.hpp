@@ -129,6 +129,14 @@ struct pmgx_ctx
   unsigned int* d_counter = nullptr;  // last-block-done counters
   double* d_partials = nullptr;       // [max_blocks * 4]
   int max_red_blocks = 0;
+  // NVLink peer-memory path (one process per GPU on one node, p2p.cu): every rank maps the
+  // others' exchange buffers with CUDA IPC; halo values and all-reduce operands are stored
+  // straight into the peer's memory by our own kernels, completion is signalled with epoch flags.
+  bool p2p = false;
+  double* ar_local = nullptr;             // [2][nranks][4] operands + nranks uint64 epoch flags
+  double** d_ar_peers = nullptr;          // device array [nranks]: every rank's ar_local, mapped here
+  std::vector<void*> p2p_mapped;          // IPC mappings to close at destroy
+  unsigned long long ar_epoch = 0;
   long long launches = 0;
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[PMGX_MAX_DEGREE + 1];
@@ -151,6 +159,19 @@ inline void check_launch(const char* what)
 void gll_points_weights(int n, std::vector<double>& x, std::vector<double>& w);
 void gll_deriv_matrix(const std::vector<double>& x, std::vector<double>& D); // D[q*n+i]
 void gll_interp_matrix(int pc, int pf, std::vector<double>& M);              // M[f*(pc+1)+c]
+
+// NVLink peer-memory plumbing (p2p.cu)
+namespace p2p
+{
+// collective over all ranks: every rank contributes `bytes`, all[r*bytes ...] is rank r's block
+void allgather_bytes(pmgx_ctx* c, const void* mine, size_t bytes, std::vector<char>& all);
+// collective: true iff `mine` is true on every rank
+bool all_agree(pmgx_ctx* c, bool mine);
+void ctx_setup(pmgx_ctx* c);    // maps the all-reduce slots of all ranks; leaves c->p2p false on failure
+void ctx_teardown(pmgx_ctx* c);
+// sum / max of d_scalars[slot .. slot+count) over ranks, in place, on the compute stream
+void allreduce(pmgx_ctx* c, int slot, int count, bool is_max);
+} // namespace p2p
 
 // vector kernels (vector_ops.cu) -- device-scalar flavoured internals used by the solvers
 namespace vec

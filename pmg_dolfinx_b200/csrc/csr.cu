@@ -59,6 +59,40 @@ k_spmv(int n_rows, const double* __restrict__ vals, const int32_t* __restrict__ 
     y[row] = ACCUM ? y[row] + s : s;
 }
 
+// ghost-column block of the rows that have one (the rows of dofs on a partition interface):
+// y[row] += sum over [off_diag[row], row_ptr[row+1])
+__global__ void __launch_bounds__(ST)
+k_spmv_ghost_rows(int n_list, const int32_t* __restrict__ rows, const double* __restrict__ vals,
+                  const int32_t* __restrict__ off_diag, const int32_t* __restrict__ row_ptr,
+                  const int32_t* __restrict__ cols, const double* __restrict__ x, double* __restrict__ y)
+{
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const int li = gt / LPR, lane = gt % LPR;
+  double s = 0.0;
+  int row = -1;
+  if (li < n_list)
+  {
+    row = rows[li];
+    const int e = row_ptr[row + 1];
+    for (int j = off_diag[row] + lane; j < e; j += LPR)
+      s = fma(vals[j], x[cols[j]], s);
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1)
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (row >= 0 && lane == 0)
+    y[row] += s;
+}
+
+__global__ void k_flag_ghost_rows(int n_rows, const int32_t* __restrict__ off_diag,
+                                  const int32_t* __restrict__ row_ptr, int32_t* __restrict__ count,
+                                  int32_t* __restrict__ list)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_rows && off_diag[i] < row_ptr[i + 1])
+    list[atomicAdd(count, 1)] = i;
+}
+
 __global__ void k_extract_diag_inv(int n_rows, const double* __restrict__ vals,
                                    const int32_t* __restrict__ row_ptr,
                                    const int32_t* __restrict__ cols, double* __restrict__ dinv)
@@ -91,16 +125,33 @@ void CsrOperator::apply(double* x, double* y)
   }
   if (halo)
     halo_fwd_end(halo, x);                                                         // :262
-  if (n_owned > 0 && has_ghost_cols)
+  if (n_ghost_rows > 0)
   {
-    k_spmv<true><<<grid, ST, 0, ctx->stream>>>(n_owned, values.p, off_diag.p, row_ptr.p + 1, cols.p, x, y); // :264-268
-    check_launch("k_spmv");
+    // :264-268, restricted to the rows that own a ghost-column entry
+    const int g2 = (int)(((long long)n_ghost_rows * LPR + ST - 1) / ST);
+    k_spmv_ghost_rows<<<g2, ST, 0, ctx->stream>>>(n_ghost_rows, ghost_rows.p, values.p, off_diag.p, row_ptr.p, cols.p,
+                                                  x, y);
+    check_launch("k_spmv_ghost_rows");
     count_launch(ctx);
   }
 }
 
 void CsrOperator::finish_setup()
 {
+  n_ghost_rows = 0;
+  if (n_owned > 0 && has_ghost_cols)
+  {
+    DevBuf<int32_t> count;
+    count.alloc(1);
+    ghost_rows.alloc((size_t)n_owned);
+    PMGX_CUDA(cudaMemsetAsync(count.p, 0, sizeof(int32_t), ctx->stream));
+    k_flag_ghost_rows<<<(n_owned + 255) / 256, 256, 0, ctx->stream>>>(n_owned, off_diag.p, row_ptr.p, count.p,
+                                                                      ghost_rows.p);
+    check_launch("k_flag_ghost_rows");
+    PMGX_CUDA(cudaMemcpyAsync(&n_ghost_rows, count.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PMGX_CUDA(cudaStreamSynchronize(ctx->stream));
+    // the compaction order is arbitrary; every row appears once, so the result does not depend on it
+  }
   diag_inv.alloc((size_t)n_owned);
   if (n_owned > 0)
   {

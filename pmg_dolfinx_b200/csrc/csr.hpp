@@ -12,6 +12,8 @@ struct CsrOperator : pmgx_operator
   DevBuf<int32_t> off_diag; // n_owned: first ghost-column entry of each row (src/csr.hpp:118-121)
   DevBuf<int32_t> cols;
   DevBuf<double> values;
+  DevBuf<int32_t> ghost_rows; // rows with at least one ghost-column entry
+  int n_ghost_rows = 0;
   void apply(double* x, double* y) override;
   void finish_setup(); // extracts diag^-1 (src/csr.hpp:101-112)
 };

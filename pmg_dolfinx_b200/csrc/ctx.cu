@@ -42,7 +42,13 @@ int pmgx_ctx_create(int device, int rank, int nranks, const void* nccl_id_h, pmg
   c->nranks = nranks;
   c->num_sms = prop.multiProcessorCount;
   PMGX_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  PMGX_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  {
+    // the halo stream outranks the compute stream: its small pack / unpack kernels must not queue
+    // behind the CTAs of a long interior-cell kernel
+    int lo = 0, hi = 0;
+    PMGX_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    PMGX_CUDA(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, hi));
+  }
   PMGX_CUDA(cudaMalloc(&c->d_scalars, 64 * sizeof(double)));
   PMGX_CUDA(cudaMemset(c->d_scalars, 0, 64 * sizeof(double)));
   PMGX_CUDA(cudaMallocHost(&c->h_scalars, 64 * sizeof(double)));
@@ -55,6 +61,7 @@ int pmgx_ctx_create(int device, int rank, int nranks, const void* nccl_id_h, pmg
     ncclUniqueId id;
     std::memcpy(&id, nccl_id_h, sizeof(id));
     PMGX_NCCL(ncclCommInitRank(&c->comm, nranks, id, rank));
+    pmgx::p2p::ctx_setup(c); // NVLink peer-memory path; NCCL stays the fallback
   }
   *out = c;
   PMGX_API_END
@@ -67,6 +74,7 @@ int pmgx_ctx_destroy(pmgx_ctx* c)
     return PMGX_OK;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
+  pmgx::p2p::ctx_teardown(c);
   if (c->comm)
     ncclCommDestroy(c->comm);
   cudaFree(c->d_scalars);
@@ -121,6 +129,7 @@ int pmgx_ctx_profile_read(pmgx_ctx* c, int degree, double* ms_total_h, long long
 
 void* pmgx_ctx_stream(pmgx_ctx* c) { return c ? (void*)c->stream : nullptr; }
 int pmgx_ctx_rank(pmgx_ctx* c) { return c ? c->rank : -1; }
+int pmgx_ctx_uses_p2p(pmgx_ctx* c) { return c && c->p2p ? 1 : 0; }
 int pmgx_ctx_nranks(pmgx_ctx* c) { return c ? c->nranks : -1; }
 long long pmgx_ctx_launch_count(pmgx_ctx* c) { return c ? c->launches : -1; }
 }

@@ -7,6 +7,9 @@
 #include "common.hpp"
 #include "operator.hpp"
 
+#include <algorithm>
+#include <cstring>
+
 namespace pmgx
 {
 namespace
@@ -40,7 +43,94 @@ __global__ void k_unpack_add(int n, const int32_t* __restrict__ idx, const doubl
     atomicAdd(&out[idx[i]], in[i]);
 }
 constexpr int PT = 256;
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
+{
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Pack + send in one kernel: entry i of the send list is stored straight into the destination
+// rank's receive buffer over NVLink; the last CTA to finish releases this rank's epoch flag on
+// every destination (system-scope fence before the ticket, so all CTAs' stores are ordered first).
+__global__ void __launch_bounds__(PT)
+k_pack_p2p(int ns, int n_nbr, const int* __restrict__ send_offsets, const int32_t* __restrict__ idx,
+           const double* __restrict__ x, const double* __restrict__ sub, double* const* __restrict__ peer_dst,
+           const long long* __restrict__ peer_stride, unsigned long long* const* __restrict__ peer_flag,
+           unsigned long long epoch, unsigned int* ticket)
+{
+  __shared__ bool is_last;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < ns)
+  {
+    int nb = 0;
+    while (i >= send_offsets[nb + 1])
+      ++nb;
+    const int32_t d = idx[i];
+    const double v = sub ? sub[d] * (-1.0) + x[d] : x[d];
+    peer_dst[nb][(long long)(epoch & 1ull) * peer_stride[nb] + (i - send_offsets[nb])] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0)
+    is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!is_last)
+    return;
+  __threadfence_system();
+  if ((int)threadIdx.x < n_nbr)
+    st_release_sys(peer_flag[threadIdx.x], epoch);
+  if (threadIdx.x == 0)
+    *ticket = 0u;
+}
+
+// One small CTA that waits until every source rank has released this epoch; the unpack kernel
+// behind it in the stream then only runs once the data is here (no spinning CTAs holding SMs
+// that the interior-cell kernel wants).
+__global__ void k_wait_p2p(int n_nbr, const unsigned long long* __restrict__ flags, unsigned long long epoch)
+{
+  for (int t = threadIdx.x; t < n_nbr; t += blockDim.x)
+    while (ld_acquire_sys(flags + t) < epoch)
+      __nanosleep(64);
+}
+
+__global__ void k_unpack_cg(int n, const int32_t* __restrict__ idx, const double* __restrict__ in,
+                            double* __restrict__ out)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    out[idx[i]] = __ldcg(in + i); // written by a remote GPU: bypass L1
+}
 } // namespace
+
+static void halo_fwd_begin_p2p(pmgx_halo* h, double* x, const double* sub)
+{
+  pmgx_ctx* c = h->ctx;
+  const int ns = h->n_send(), nr = h->n_recv();
+  ++h->epoch;
+  if (ns > 0)
+  {
+    k_pack_p2p<<<(ns + PT - 1) / PT, PT, 0, c->comm_stream>>>(ns, (int)h->send_ranks.size(), h->d_send_offsets.p,
+                                                             h->send_idx.p, x, sub, h->d_peer_dst.p, h->d_peer_stride.p,
+                                                             h->d_peer_flag.p, h->epoch, h->d_ticket.p);
+    check_launch("k_pack_p2p");
+    count_launch(c);
+  }
+  if (nr > 0)
+  {
+    const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(h->xbuf + 2 * (size_t)std::max(nr, 1));
+    k_wait_p2p<<<1, 32, 0, c->comm_stream>>>((int)h->recv_ranks.size(), flags, h->epoch);
+    k_unpack_cg<<<(nr + PT - 1) / PT, PT, 0, c->comm_stream>>>(nr, h->recv_idx.p, h->xbuf + (h->epoch & 1ull) * (size_t)nr,
+                                                              x + h->n_owned);
+    check_launch("k_unpack(p2p)");
+    count_launch(c, 2);
+  }
+}
 
 void halo_fwd_begin(pmgx_halo* h, double* x, const double* sub)
 {
@@ -50,6 +140,13 @@ void halo_fwd_begin(pmgx_halo* h, double* x, const double* sub)
     return;
   PMGX_CUDA(cudaEventRecord(h->ev_ready, c->stream));
   PMGX_CUDA(cudaStreamWaitEvent(c->comm_stream, h->ev_ready, 0));
+  if (h->p2p)
+  {
+    halo_fwd_begin_p2p(h, x, sub);
+    PMGX_CUDA(cudaEventRecord(h->ev_done, c->comm_stream));
+    h->in_flight = true;
+    return;
+  }
   if (ns > 0)
   {
     if (sub)
@@ -87,6 +184,94 @@ void halo_fwd_end(pmgx_halo* h, double* x)
     return;
   PMGX_CUDA(cudaStreamWaitEvent(h->ctx->stream, h->ev_done, 0));
   h->in_flight = false;
+}
+
+// Maps the receive buffers of the neighbours (CUDA IPC) so that k_pack_p2p can store into them.
+// Every rank publishes: the IPC handle of its xbuf, its n_recv, and for every possible source
+// rank the offset of that source's segment in the receive buffer and its flag index (-1: none).
+void halo_setup_p2p(pmgx_halo* h)
+{
+  pmgx_ctx* c = h->ctx;
+  const int R = c->nranks, nr = h->n_recv();
+  // the flag handshake needs a symmetric neighbourhood (true for ghost-layer halos)
+  std::vector<int> a(h->send_ranks), b(h->recv_ranks);
+  std::sort(a.begin(), a.end());
+  std::sort(b.begin(), b.end());
+  bool ok = a == b;
+  const size_t bytes = (2 * (size_t)std::max(nr, 1) + std::max<size_t>(h->recv_ranks.size(), 1)) * sizeof(double);
+  cudaIpcMemHandle_t hd;
+  std::memset(&hd, 0, sizeof(hd));
+  if (ok)
+  {
+    ok = cudaMalloc(&h->xbuf, bytes) == cudaSuccess && cudaMemset(h->xbuf, 0, bytes) == cudaSuccess
+         && cudaIpcGetMemHandle(&hd, h->xbuf) == cudaSuccess;
+    cudaGetLastError();
+  }
+  const size_t rec = sizeof(hd) + sizeof(long long) * (1 + 2 * (size_t)R);
+  std::vector<char> mine(rec, 0), all;
+  std::memcpy(mine.data(), &hd, sizeof(hd));
+  long long* tab = reinterpret_cast<long long*>(mine.data() + sizeof(hd));
+  tab[0] = nr;
+  for (int r = 0; r < R; ++r)
+    tab[1 + r] = -1, tab[1 + R + r] = -1;
+  for (size_t i = 0; i < h->recv_ranks.size(); ++i)
+  {
+    tab[1 + h->recv_ranks[i]] = h->recv_offsets[i];
+    tab[1 + R + h->recv_ranks[i]] = (long long)i;
+  }
+  p2p::allgather_bytes(c, mine.data(), rec, all);
+  ok = p2p::all_agree(c, ok);
+  const size_t nn = h->send_ranks.size();
+  std::vector<double*> dst(nn, nullptr);
+  std::vector<long long> stride(nn, 0);
+  std::vector<unsigned long long*> flag(nn, nullptr);
+  for (size_t i = 0; i < nn && ok; ++i)
+  {
+    const int p = h->send_ranks[i];
+    const char* recp = all.data() + (size_t)p * rec;
+    cudaIpcMemHandle_t hp;
+    std::memcpy(&hp, recp, sizeof(hp));
+    const long long* tp = reinterpret_cast<const long long*>(recp + sizeof(hp));
+    const long long p_nr = tp[0], off = tp[1 + c->rank], fidx = tp[1 + R + c->rank];
+    const int seg = h->send_offsets[i + 1] - h->send_offsets[i];
+    if (off < 0 || fidx < 0 || off + seg > p_nr)
+    {
+      ok = false;
+      break;
+    }
+    void* base = nullptr;
+    if (cudaIpcOpenMemHandle(&base, hp, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+    {
+      cudaGetLastError();
+      ok = false;
+      break;
+    }
+    h->mapped.push_back(base);
+    dst[i] = static_cast<double*>(base) + off;
+    stride[i] = p_nr;
+    flag[i] = reinterpret_cast<unsigned long long*>(static_cast<double*>(base) + 2 * (size_t)std::max<long long>(p_nr, 1)) + fidx;
+  }
+  ok = p2p::all_agree(c, ok);
+  if (!ok)
+  {
+    for (void* p : h->mapped)
+      cudaIpcCloseMemHandle(p);
+    h->mapped.clear();
+    if (h->xbuf)
+      cudaFree(h->xbuf);
+    h->xbuf = nullptr;
+    h->p2p = false;
+    cudaGetLastError();
+    return;
+  }
+  h->d_peer_dst.upload(dst.data(), nn, c->stream);
+  h->d_peer_stride.upload(stride.data(), nn, c->stream);
+  h->d_peer_flag.upload(flag.data(), nn, c->stream);
+  h->d_send_offsets.upload(h->send_offsets.data(), h->send_offsets.size(), c->stream);
+  h->d_ticket.alloc(1);
+  PMGX_CUDA(cudaMemsetAsync(h->d_ticket.p, 0, sizeof(unsigned int), c->stream));
+  PMGX_CUDA(cudaStreamSynchronize(c->stream));
+  h->p2p = true;
 }
 
 static void halo_rev(pmgx_halo* h, double* x)
@@ -170,6 +355,8 @@ int pmgx_halo_create(pmgx_ctx* ctx, int n_owned, int n_ghost, int n_send_nbr,
   h->recv_buf.alloc(nr);
   PMGX_CUDA(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
   PMGX_CUDA(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+  if (ctx->p2p)
+    pmgx::halo_setup_p2p(h.get()); // collective over all ranks (every rank creates its halos in the same order)
   *out = h.release();
   PMGX_API_END
 }
@@ -186,10 +373,16 @@ int pmgx_halo_destroy(pmgx_halo* h)
       cudaEventDestroy(h->ev_ready);
     if (h->ev_done)
       cudaEventDestroy(h->ev_done);
+    for (void* p : h->mapped)
+      cudaIpcCloseMemHandle(p);
+    if (h->xbuf)
+      cudaFree(h->xbuf);
     delete h;
   }
   PMGX_API_END
 }
+
+int pmgx_halo_uses_p2p(pmgx_halo* h) { return h && h->p2p ? 1 : 0; }
 
 int pmgx_halo_fwd_begin(pmgx_halo* h, double* x)
 {

@@ -14,6 +14,17 @@ struct pmgx_halo
   cudaEvent_t ev_ready = nullptr; // compute stream -> comm stream (x is ready to pack)
   cudaEvent_t ev_done = nullptr;  // comm stream -> compute stream (ghosts are in place)
   bool in_flight = false;
+  // NVLink peer-memory path (halo.cu, p2p.cu): packed values are stored straight into the
+  // destination rank's receive buffer; an epoch flag per source rank signals completion
+  bool p2p = false;
+  double* xbuf = nullptr;                        // IPC-shared: [2][n_recv] doubles, then one uint64 flag per source
+  pmgx::DevBuf<double*> d_peer_dst;              // per destination: its xbuf + the offset of my segment there
+  pmgx::DevBuf<long long> d_peer_stride;         // per destination: its n_recv (distance between its two buffers)
+  pmgx::DevBuf<unsigned long long*> d_peer_flag; // per destination: my flag in its xbuf
+  pmgx::DevBuf<int> d_send_offsets;              // n_send_nbr + 1
+  pmgx::DevBuf<unsigned int> d_ticket;
+  std::vector<void*> mapped;
+  unsigned long long epoch = 0;
   int n_send() const { return send_offsets.empty() ? 0 : send_offsets.back(); }
   int n_recv() const { return recv_offsets.empty() ? 0 : recv_offsets.back(); }
 };
@@ -23,6 +34,7 @@ namespace pmgx
 // sub (may be null): the owners send x - sub instead of x (ghost block of x receives it)
 void halo_fwd_begin(pmgx_halo* h, double* x, const double* sub = nullptr);
 void halo_fwd_end(pmgx_halo* h, double* x);
+void halo_setup_p2p(pmgx_halo* h);
 } // namespace pmgx
 
 // Operator concept of the reference (operator()(in,out) + get_diag_inverse,

@@ -222,9 +222,7 @@ static int red_grid(pmgx_ctx* c, long long n)
 
 void allreduce_scalars(pmgx_ctx* c, int slot, int count, bool is_max)
 {
-  if (c->nranks > 1)
-    PMGX_NCCL(ncclAllReduce(c->d_scalars + slot, c->d_scalars + slot, count, ncclDouble,
-                            is_max ? ncclMax : ncclSum, c->comm, c->stream));
+  p2p::allreduce(c, slot, count, is_max); // peer-memory kernel over NVLink, NCCL when unavailable
 }
 
 void dot_device(pmgx_ctx* c, const double* a, const double* b, long long n, int slot)

@@ -63,6 +63,10 @@ def main():
         op = api.MatFreeLaplacian(ctx, P, kappa, dm, xgeom, gdm, mesh.lcells, mesh.bcells, bc, sp.n_owned, sp.n_ghost, halo)
         lv.append(dict(P=P, sp=sp, halo=halo, dm=dm, bc=bc, op=op))
 
+    if rank == 0:
+        paths = {bool(api.lib.pmgx_halo_uses_p2p(d["halo"].h)) for d in lv} | {bool(api.lib.pmgx_ctx_uses_p2p(ctx.h))}
+        print("halo path: " + ("nvlink-p2p" if paths == {True} else "nccl" if paths == {False} else "mixed"), flush=True)
+
     # ---------------- oracle on rank 0 (single domain, same geometry)
     ok = True
     if rank == 0:

@@ -10,14 +10,17 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.mark.parametrize("p2p", ["1", "0"], ids=["nvlink-p2p", "nccl"])
 @pytest.mark.parametrize("nranks", [2, 4, 8])
-def test_multi_gpu_matches_oracle(nranks):
+def test_multi_gpu_matches_oracle(nranks, p2p):
     import torch
     if not torch.cuda.is_available() or torch.cuda.device_count() < nranks:
         pytest.skip(f"needs {nranks} GPUs")
-    port = 29600 + nranks
+    port = 29600 + nranks + 20 * int(p2p)
+    env = dict(os.environ, PMGX_P2P=p2p)   # "0": NCCL send/recv + ncclAllReduce instead of the peer-memory kernels
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nranks}",
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "scripts", "mgpu_check.py")]
-    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert f"[mgpu x{nranks}] PASS" in r.stdout
+    assert ("halo path: nvlink-p2p" if p2p == "1" else "halo path: nccl") in r.stdout
