@@ -42,6 +42,16 @@ def b_apply(P, ncells, ndofs):
     return ncells * ((P + 1) ** 3 * 52 + 8) + ndofs * 17
 
 
+def measured_traffic(P, ncells):
+    """DRAM bytes of one apply launch from the committed ncu --set full capture (profiles/), scaled
+    by the number of cells if this run's launch differs from the captured one; None if absent."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "apply_traffic.json")))[str(P)]
+        return (t["dram_bytes_read"] + t["dram_bytes_write"]) * ncells / t["cells"], t["source"]
+    except Exception:
+        return None, None
+
+
 def measured_peak():
     try:
         pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -310,7 +320,7 @@ def run_gpu(args):
     bb = [b, api.Vector(ctx, sp.n_owned, sp.n_ghost, halo_top)]
     us = [torch.empty(n_owned, dtype=torch.float64, device=ctx.device) for _ in range(2)]
     s_up, s_down = torch.cuda.Stream(device=ctx.device), torch.cuda.Stream(device=ctx.device)
-    e2e_steps = max(2, min(args.steps, 4))
+    e2e_steps = max(4, args.steps)
 
     def e2e_loop(nsteps, e_begin=None, e_end=None):
         up = [torch.cuda.Event() for _ in range(nsteps)]      # b of step i is on the device
@@ -360,6 +370,7 @@ def run_gpu(args):
         n_applies = kl.value / launches_per_apply
         B = b_apply(Ptop, n_own_cells, n_owned)
         achieved = B * n_applies / (kms.value * 1e-3) / 1e9 if kms.value > 0 else None
+        traffic, traffic_src = measured_traffic(Ptop, n_own_cells)
         cb = cpu_baseline(n=args.cpu_cells) if world == 1 and not args.no_cpu else None
         line = {
             "metric": METRIC, "value": nd_global / ms_per_step / 1e6, "unit": "Gdof/s", "n_gpus": world,
@@ -371,12 +382,16 @@ def run_gpu(args):
                        "smoother": f"Chebyshev-4 Jacobi, {NSMOOTH} its", "lambda_max": eigs,
                        "coarse": f"CSR Jacobi-PCG <= {COARSE_ITS} its, rtol {COARSE_RTOL}",
                        "l2": "working set >> 126 MB L2, no flush needed",
+                       "coarse_iterations_last_cycle": int(api.lib.pmgx_coarse_last_iterations(keep[5].h)),
+                       "halo": "nvlink-p2p" if api.lib.pmgx_ctx_uses_p2p(ctx.h) else ("nccl" if world > 1 else "none"),
                        "residual_reduction_after_cycles": [args.warmup + args.steps + 1, rn / rn0]},
             "apply": {"degree": Ptop, "ms": apply_ms, "gdofs": nd_global / apply_ms / 1e6,
                       "gbs_algorithmic": B / apply_ms / 1e6, "frac_of_hbm_peak": B / apply_ms / 1e6 / peak,
                       "note": "operator()(x,y) incl. zero fill of y and halo; max over ranks"},
-            "roofline": {"bound": "hbm", "kernel": f"k_apply<{Ptop}>", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak if achieved else None, "traffic": None,
+            "roofline": {"bound": "hbm", "kernel": f"k_apply_tma<{Ptop},128,2>", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak if achieved else None,
+                         "traffic": traffic,
+                         "traffic_source": traffic_src,
                          "peak_source": peak_src, "launches_timed": kl.value,
                          "algorithmic_bytes_per_apply": B, "avg_launch_ms": kms.value / max(kl.value, 1)},
             "e2e": {"value": nd_global / e2e_ms / 1e6, "unit": "Gdof/s", "ms_per_step": e2e_ms, "steps": e2e_steps,

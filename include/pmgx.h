@@ -233,6 +233,9 @@ int pmgx_interp_destroy(pmgx_interp* it);
 int pmgx_coarse_create(pmgx_ctx* ctx, pmgx_operator* A_csr, int max_iter, double rtol,
                        pmgx_coarse** out);
 int pmgx_coarse_solve(pmgx_coarse* cs, double* x, const double* b, int* iters_h);
+/* iterations of the most recent solve (stand-alone or inside pmgx_vcycle_apply); the host looks at
+ * the residual every 8 iterations, so the count is a multiple of 8 or max_iter */
+int pmgx_coarse_last_iterations(pmgx_coarse* cs);
 int pmgx_coarse_destroy(pmgx_coarse* cs);
 
 /* ------------------------------------------------------------------ V-cycle -- */

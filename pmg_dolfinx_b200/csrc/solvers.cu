@@ -490,6 +490,7 @@ struct pmgx_coarse
   pmgx_ctx* ctx = nullptr;
   pmgx_operator* A = nullptr;
   pmgx_cg* cg = nullptr;
+  int last_iters = 0;
 };
 
 // ----------------------------------------------------------------------------- V-cycle --
@@ -724,10 +725,13 @@ int pmgx_coarse_solve(pmgx_coarse* cs, double* x, const double* b, int* iters_h)
   PMGX_REQUIRE(cs && x && b, "coarse_solve: null argument");
   PMGX_CUDA(cudaSetDevice(cs->ctx->device));
   const int k = pmgx::cgcg_solve(cs->cg, cs->A, x, b, 8, false);
+  cs->last_iters = k;
   if (iters_h)
     *iters_h = k;
   PMGX_API_END
 }
+int pmgx_coarse_last_iterations(pmgx_coarse* cs) { return cs ? cs->last_iters : -1; }
+
 int pmgx_coarse_destroy(pmgx_coarse* cs)
 {
   PMGX_API_BEGIN
@@ -858,7 +862,7 @@ int pmgx_vcycle_apply(pmgx_vcycle* v, const double* b_in, double* u_inout, doubl
   const pmgx::ChebResidual post = literal_seq ? pmgx::CHEB_R_FULL : pmgx::CHEB_R_NONE;
   if (v->coarse && nl > 1)
   {
-    pmgx::cgcg_solve(v->coarse->cg, v->coarse->A, U[0], B[0], 8, true);           // :106-107 (u[0] = 0)
+    v->coarse->last_iters = pmgx::cgcg_solve(v->coarse->cg, v->coarse->A, U[0], B[0], 8, true); // :106-107 (u[0] = 0)
   }
   else
     pmgx::cheb_solve(v->smoothers[0], v->ops[0], U[0], B[0], nullptr, !literal_seq && nl > 1, post); // :109
