@@ -56,20 +56,25 @@ k_cheb_init(const double* __restrict__ b, const double* __restrict__ q, const do
 template <bool NORM>
 __global__ void __launch_bounds__(FT)
 k_cheb_step(const double* __restrict__ q, const double* __restrict__ dinv, double* __restrict__ r,
-            double* __restrict__ z, double* __restrict__ x, double c1, double c2, bool add_x,
+            double* __restrict__ z, double* __restrict__ x, double c1, double c2, bool add_x, int defer,
             long long n, double* partials, unsigned int* counter, double* out)
 {
+  // defer: the x += z of the previous pass was postponed to this one (1), and x was zero (2)
   const long long nth = (long long)gridDim.x * blockDim.x;
   double s = 0.0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nth)
   {
     const double rv = q[i] * (-1.0) + r[i];
-    const double zs = z[i] * c1;
+    const double zo = z[i];
+    const double zs = zo * c1;
     const double zv = (rv * dinv[i]) * c2 + zs;
     r[i] = rv;
     z[i] = zv;
     if (add_x)
-      x[i] = zv * 1.0 + x[i];
+    {
+      const double xo = defer == 2 ? zo : (defer == 1 ? zo * 1.0 + x[i] : x[i]);
+      x[i] = zv * 1.0 + xo;
+    }
     if (NORM)
       s = fma(rv, rv, s);
   }
@@ -107,15 +112,18 @@ k_cheb_last(const double* __restrict__ q, double* __restrict__ r, long long n, d
 template <int DUMMY>
 __global__ void __launch_bounds__(FT)
 k_cheb_step_xonly(const double* __restrict__ q, const double* __restrict__ dinv, const double* __restrict__ r,
-                  const double* __restrict__ z, double* __restrict__ x, double c1, double c2, long long n)
+                  const double* __restrict__ z, double* __restrict__ x, double c1, double c2, int defer,
+                  long long n)
 {
   const long long nth = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nth)
   {
     const double rv = q[i] * (-1.0) + r[i];
-    const double zs = z[i] * c1;
+    const double zo = z[i];
+    const double zs = zo * c1;
     const double zv = (rv * dinv[i]) * c2 + zs;
-    x[i] = zv * 1.0 + x[i];
+    const double xo = defer == 2 ? zo : (defer == 1 ? zo * 1.0 + x[i] : x[i]);
+    x[i] = zv * 1.0 + xo;
   }
 }
 
@@ -281,7 +289,11 @@ void cheb_solve(pmgx_cheb* s, pmgx_operator* A, double* x, const double* b, doub
   if (!x_is_zero)
     A->apply(x, s->q.p); // :56
   const double* q0 = x_is_zero ? nullptr : s->q.p; // A*0 = 0: skip the apply, r = b
-  const bool first_add = s->max_iter >= 1;
+  // x += z0 (:73, first iteration) is postponed to the next pass whenever that pass updates x
+  // anyway: it then forms (x + z0) + z1 in the reference's order and this pass does not touch x
+  const bool deferred = s->max_iter >= 2; // then the pass of iteration 1 is never the last one
+  const bool first_add = s->max_iter >= 1 && !deferred;
+  const int defer_mode = !deferred ? 0 : (x_is_zero ? 2 : 1);
   const double c0 = 4.0 / (3.0 * lmax);
   if (hist)
     k_cheb_init<true><<<grid, FT, 0, c->stream>>>(b, q0, dinv, s->r.p, s->z.p, x, c0, first_add, n,
@@ -319,18 +331,21 @@ void cheb_solve(pmgx_cheb* s, pmgx_operator* A, double* x, const double* b, doub
     else if (i + 1 == s->max_iter && final_r == CHEB_R_NONE)
     {
       // the next iteration is dropped, so r and z of this one are dead as well
-      k_cheb_step_xonly<0><<<grid, FT, 0, c->stream>>>(s->q.p, dinv, s->r.p, s->z.p, x, c1, c2, n);
+      k_cheb_step_xonly<0><<<grid, FT, 0, c->stream>>>(s->q.p, dinv, s->r.p, s->z.p, x, c1, c2,
+                                                       i == 1 ? defer_mode : 0, n);
       check("k_cheb_step_xonly");
     }
     else
     {
       // the x += z of iteration i+1 (:73) is folded into this pass
       if (hist)
-        k_cheb_step<true><<<grid, FT, 0, c->stream>>>(s->q.p, dinv, s->r.p, s->z.p, x, c1, c2, true, n,
-                                                      c->d_partials, c->d_counter, c->d_scalars + 8);
+        k_cheb_step<true><<<grid, FT, 0, c->stream>>>(s->q.p, dinv, s->r.p, s->z.p, x, c1, c2, true,
+                                                      i == 1 ? defer_mode : 0, n, c->d_partials, c->d_counter,
+                                                      c->d_scalars + 8);
       else
-        k_cheb_step<false><<<grid, FT, 0, c->stream>>>(s->q.p, dinv, s->r.p, s->z.p, x, c1, c2, true, n,
-                                                       c->d_partials, c->d_counter, c->d_scalars + 8);
+        k_cheb_step<false><<<grid, FT, 0, c->stream>>>(s->q.p, dinv, s->r.p, s->z.p, x, c1, c2, true,
+                                                       i == 1 ? defer_mode : 0, n, c->d_partials, c->d_counter,
+                                                       c->d_scalars + 8);
       check("k_cheb_step");
     }
     count_launch(c);
