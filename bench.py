@@ -330,12 +330,17 @@ def run_gpu(args):
             e_begin.record(ctx.stream)
         s_up.wait_stream(ctx.stream)
         s_down.wait_stream(ctx.stream)
-        for i in range(nsteps):
+        def upload(i):
             with torch.cuda.stream(s_up):
                 if i >= 2:
                     s_up.wait_event(used[i - 2])               # buffer i%2 is free again
                 bb[i % 2].data[:n_owned].copy_(hb, non_blocking=True)
                 up[i].record(s_up)
+
+        upload(0)
+        for i in range(nsteps):
+            if i + 1 < nsteps:
+                upload(i + 1)   # enqueued before apply(i): the host blocks inside the cycle (coarse-solve checks)
             ctx.stream.wait_event(up[i])
             pmg.apply(bb[i % 2], u)
             if i >= 2:
