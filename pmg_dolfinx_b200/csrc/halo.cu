@@ -6,6 +6,7 @@
 // and hand device pointers to GPU-aware MPI.
 #include "common.hpp"
 #include "operator.hpp"
+#include "reduce.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -44,17 +45,6 @@ __global__ void k_unpack_add(int n, const int32_t* __restrict__ idx, const doubl
 }
 constexpr int PT = 256;
 
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
-{
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
-{
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-
 // Pack + send in one kernel: entry i of the send list is stored straight into the destination
 // rank's receive buffer over NVLink; the last CTA to finish releases this rank's epoch flag on
 // every destination (system-scope fence before the ticket, so all CTAs' stores are ordered first).
@@ -84,7 +74,7 @@ k_pack_p2p(int ns, int n_nbr, const int* __restrict__ send_offsets, const int32_
     return;
   __threadfence_system();
   if ((int)threadIdx.x < n_nbr)
-    st_release_sys(peer_flag[threadIdx.x], epoch);
+    st_release_sys_u64(peer_flag[threadIdx.x], epoch);
   if (threadIdx.x == 0)
     *ticket = 0u;
 }
@@ -95,8 +85,7 @@ k_pack_p2p(int ns, int n_nbr, const int* __restrict__ send_offsets, const int32_
 __global__ void k_wait_p2p(int n_nbr, const unsigned long long* __restrict__ flags, unsigned long long epoch)
 {
   for (int t = threadIdx.x; t < n_nbr; t += blockDim.x)
-    while (ld_acquire_sys(flags + t) < epoch)
-      __nanosleep(64);
+    wait_epoch(flags + t, epoch); // traps after ~10 s if a neighbour never arrives
 }
 
 __global__ void k_unpack_cg(int n, const int32_t* __restrict__ idx, const double* __restrict__ in,
@@ -107,6 +96,15 @@ __global__ void k_unpack_cg(int n, const int32_t* __restrict__ idx, const double
     out[idx[i]] = __ldcg(in + i); // written by a remote GPU: bypass L1
 }
 } // namespace
+
+// Stream on which work that needs the ghost values can be enqueued right behind the exchange
+// (the comm stream while an exchange is in flight, else the compute stream).  Boundary-cell
+// kernels launched there start as soon as the ghosts are in place and fill the tail of the
+// interior-cell kernel instead of waiting for it; halo_fwd_end joins the two streams.
+cudaStream_t halo_stream(pmgx_halo* h, pmgx_ctx* c)
+{
+  return (h && h->in_flight) ? c->comm_stream : c->stream;
+}
 
 static void halo_fwd_begin_p2p(pmgx_halo* h, double* x, const double* sub)
 {
@@ -143,7 +141,6 @@ void halo_fwd_begin(pmgx_halo* h, double* x, const double* sub)
   if (h->p2p)
   {
     halo_fwd_begin_p2p(h, x, sub);
-    PMGX_CUDA(cudaEventRecord(h->ev_done, c->comm_stream));
     h->in_flight = true;
     return;
   }
@@ -173,7 +170,6 @@ void halo_fwd_begin(pmgx_halo* h, double* x, const double* sub)
     check_launch("k_unpack");
     count_launch(c);
   }
-  PMGX_CUDA(cudaEventRecord(h->ev_done, c->comm_stream));
   h->in_flight = true;
 }
 
@@ -182,6 +178,9 @@ void halo_fwd_end(pmgx_halo* h, double* x)
   (void)x;
   if (!h->in_flight)
     return;
+  // everything enqueued on the comm stream so far -- the exchange and any boundary-cell work the
+  // caller put behind it (halo_stream) -- must finish before the compute stream goes on
+  PMGX_CUDA(cudaEventRecord(h->ev_done, h->ctx->comm_stream));
   PMGX_CUDA(cudaStreamWaitEvent(h->ctx->stream, h->ev_done, 0));
   h->in_flight = false;
 }

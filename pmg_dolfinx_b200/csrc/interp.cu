@@ -289,7 +289,7 @@ namespace pmgx
 namespace
 {
 template <int NC, int NF>
-void launch_prolong(pmgx_interp* it, int first, int count, const double* xc, double* xf, bool add)
+void launch_prolong(pmgx_interp* it, cudaStream_t st, int first, int count, const double* xc, double* xf, bool add)
 {
   if (count <= 0)
     return;
@@ -298,17 +298,18 @@ void launch_prolong(pmgx_interp* it, int first, int count, const double* xc, dou
   const int grid = (count + C::cpb - 1) / C::cpb;
   const int n_owned_f = it->halo_f ? it->halo_f->n_owned : it->n_fine_total;
   if (add)
-    k_prolong<NC, NF, true><<<grid, C::tpb, 0, c->stream>>>(it->tab, it->cells.p, first, count, it->dm_c, it->dm_f,
+    k_prolong<NC, NF, true><<<grid, C::tpb, 0, st>>>(it->tab, it->cells.p, first, count, it->dm_c, it->dm_f,
                                                            it->wmask.p, xc, xf, n_owned_f);
   else
-    k_prolong<NC, NF, false><<<grid, C::tpb, 0, c->stream>>>(it->tab, it->cells.p, first, count, it->dm_c, it->dm_f,
+    k_prolong<NC, NF, false><<<grid, C::tpb, 0, st>>>(it->tab, it->cells.p, first, count, it->dm_c, it->dm_f,
                                                             it->wmask.p, xc, xf, n_owned_f);
   check_launch("k_prolong");
   count_launch(c);
 }
 
 template <int NC, int NF>
-void launch_restrict(pmgx_interp* it, int first, int count, const double* xf, const double* sub, double* xc)
+void launch_restrict(pmgx_interp* it, cudaStream_t st, int first, int count, const double* xf, const double* sub,
+                     double* xc)
 {
   if (count <= 0)
     return;
@@ -316,7 +317,7 @@ void launch_restrict(pmgx_interp* it, int first, int count, const double* xf, co
   using C = XferCfg<NC, NF>;
   const int grid = (count + C::cpb - 1) / C::cpb;
   const int n_owned_f = it->halo_f ? it->halo_f->n_owned : it->n_fine_total;
-  k_restrict<NC, NF><<<grid, C::tpb, 0, c->stream>>>(it->tab, it->cells.p, first, count, it->dm_c, it->dm_f, xf, sub,
+  k_restrict<NC, NF><<<grid, C::tpb, 0, st>>>(it->tab, it->cells.p, first, count, it->dm_c, it->dm_f, xf, sub,
                                                      n_owned_f, it->inv_mult.p, xc);
   check_launch("k_restrict");
   count_launch(c);
@@ -357,35 +358,41 @@ void dispatch(int nc, int nf, F&& f)
 }
 } // namespace
 
-// interpolate (src/interpolate.hpp:185-239); add: fine += P coarse on owned fine dofs
+// interpolate (src/interpolate.hpp:185-239); add: fine += P coarse on owned fine dofs.
+// Interior cells run on the compute stream while the coarse halo is in flight (:202-208); the
+// boundary cells (:217-227) are enqueued right behind the exchange on the halo stream (every
+// fine dof has one writer, so the two launches never touch the same entry).
 void interp_prolong(pmgx_interp* it, double* coarse, double* fine, bool add)
 {
   pmgx_ctx* c = it->ctx;
   PMGX_CUDA(cudaSetDevice(c->device));
   if (it->halo_c)
-    halo_fwd_begin(it->halo_c, coarse);                                              // :202
+    halo_fwd_begin(it->halo_c, coarse);
+  cudaStream_t bs = halo_stream(it->halo_c, c);
   dispatch(it->pc + 1, it->pf + 1, [&](auto NC, auto NF)
-           { launch_prolong<NC(), NF()>(it, 0, it->n_l, coarse, fine, add); });        // :208
+           { launch_prolong<NC(), NF()>(it, c->stream, 0, it->n_l, coarse, fine, add); });
+  dispatch(it->pc + 1, it->pf + 1, [&](auto NC, auto NF)
+           { launch_prolong<NC(), NF()>(it, bs, it->n_l, it->n_b, coarse, fine, add); });
   if (it->halo_c)
-    halo_fwd_end(it->halo_c, coarse);                                                // :217
-  dispatch(it->pc + 1, it->pf + 1, [&](auto NC, auto NF)
-           { launch_prolong<NC(), NF()>(it, it->n_l, it->n_b, coarse, fine, add); });  // :227
+    halo_fwd_end(it->halo_c, coarse);
 }
 
-// reverse_interpolate (src/interpolate.hpp:245-303) of fine - sub (sub may be null)
+// reverse_interpolate (src/interpolate.hpp:245-303) of fine - sub (sub may be null).  The output
+// is zeroed (:270) before the exchange starts so that both launches may accumulate into it.
 void interp_restrict(pmgx_interp* it, double* fine, const double* sub, double* coarse)
 {
   pmgx_ctx* c = it->ctx;
   PMGX_CUDA(cudaSetDevice(c->device));
+  PMGX_CUDA(cudaMemsetAsync(coarse, 0, (size_t)it->n_coarse_total * sizeof(double), c->stream));
   if (it->halo_f)
     halo_fwd_begin(it->halo_f, fine, sub);                                           // :264
-  PMGX_CUDA(cudaMemsetAsync(coarse, 0, (size_t)it->n_coarse_total * sizeof(double), c->stream)); // :270
+  cudaStream_t bs = halo_stream(it->halo_f, c);
   dispatch(it->pc + 1, it->pf + 1, [&](auto NC, auto NF)
-           { launch_restrict<NC(), NF()>(it, 0, it->n_l, fine, sub, coarse); });
+           { launch_restrict<NC(), NF()>(it, c->stream, 0, it->n_l, fine, sub, coarse); });
+  dispatch(it->pc + 1, it->pf + 1, [&](auto NC, auto NF)
+           { launch_restrict<NC(), NF()>(it, bs, it->n_l, it->n_b, fine, sub, coarse); });
   if (it->halo_f)
     halo_fwd_end(it->halo_f, fine);                                                  // :281
-  dispatch(it->pc + 1, it->pf + 1, [&](auto NC, auto NF)
-           { launch_restrict<NC(), NF()>(it, it->n_l, it->n_b, fine, sub, coarse); });
 }
 } // namespace pmgx
 

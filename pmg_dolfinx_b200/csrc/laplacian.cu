@@ -492,9 +492,10 @@ k_apply(const double* __restrict__ x, double* __restrict__ y, const double* __re
 }
 
 template <int P>
-void launch_apply(pmgx_ctx* c, const double* x, double* y, const double* G, const int32_t* enc,
+void launch_apply(pmgx_ctx* c, cudaStream_t st, const double* x, double* y, const double* G, const int32_t* enc,
                   const int32_t* perm, const double* kappa, int first, int count)
 {
+  const bool timed = c->profiling && st == c->stream; // launches on the halo stream overlap the interior kernel
   if (count <= 0)
     return;
   using C = ApplyCfg<P>;
@@ -507,18 +508,18 @@ void launch_apply(pmgx_ctx* c, const double* x, double* y, const double* G, cons
   }
   const int grid = (count + C::cpb - 1) / C::cpb;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (c->profiling)
+  if (timed)
   {
     PMGX_CUDA(cudaEventCreate(&e0));
     PMGX_CUDA(cudaEventCreate(&e1));
-    PMGX_CUDA(cudaEventRecord(e0, c->stream));
+    PMGX_CUDA(cudaEventRecord(e0, st));
   }
-  k_apply<P><<<grid, C::tpb, smem, c->stream>>>(x, y, G, enc, perm, kappa, first, count);
+  k_apply<P><<<grid, C::tpb, smem, st>>>(x, y, G, enc, perm, kappa, first, count);
   check_launch("k_apply");
   count_launch(c);
-  if (c->profiling)
+  if (timed)
   {
-    PMGX_CUDA(cudaEventRecord(e1, c->stream));
+    PMGX_CUDA(cudaEventRecord(e1, st));
     c->prof[P].emplace_back(e0, e1);
   }
 }
@@ -702,9 +703,10 @@ constexpr int slab_minb()
 }
 
 template <int P>
-void launch_apply_slab(pmgx_ctx* c, const double* x, double* y, const double* G, const int32_t* enc,
+void launch_apply_slab(pmgx_ctx* c, cudaStream_t st, const double* x, double* y, const double* G, const int32_t* enc,
                        const int32_t* perm, const double* kappa, long long batch0, int cell0, int count)
 {
+  const bool timed = c->profiling && st == c->stream;
   if (count <= 0)
     return;
   using C = SlabCfg<P>;
@@ -718,18 +720,18 @@ void launch_apply_slab(pmgx_ctx* c, const double* x, double* y, const double* G,
   }
   const int grid = (count + C::cpb - 1) / C::cpb;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (c->profiling)
+  if (timed)
   {
     PMGX_CUDA(cudaEventCreate(&e0));
     PMGX_CUDA(cudaEventCreate(&e1));
-    PMGX_CUDA(cudaEventRecord(e0, c->stream));
+    PMGX_CUDA(cudaEventRecord(e0, st));
   }
-  k_apply_slab<P, MINB><<<grid, C::tpb, C::smem, c->stream>>>(x, y, G, enc, perm, kappa, batch0, cell0, count);
+  k_apply_slab<P, MINB><<<grid, C::tpb, C::smem, st>>>(x, y, G, enc, perm, kappa, batch0, cell0, count);
   check_launch("k_apply_slab");
   count_launch(c);
-  if (c->profiling)
+  if (timed)
   {
-    PMGX_CUDA(cudaEventRecord(e1, c->stream));
+    PMGX_CUDA(cudaEventRecord(e1, st));
     c->prof[P].emplace_back(e0, e1);
   }
 }
@@ -1030,9 +1032,10 @@ k_apply_tma(const double* __restrict__ x, double* __restrict__ y, const double* 
 }
 
 template <int P, int TPB, int R>
-void launch_apply_tma_t(pmgx_ctx* c, const double* x, double* y, const double* G, const int32_t* enc,
+void launch_apply_tma_t(pmgx_ctx* c, cudaStream_t st, const double* x, double* y, const double* G, const int32_t* enc,
                         const int32_t* perm, const double* kappa, long long batch0, int cell0, int count)
 {
+  const bool timed = c->profiling && st == c->stream;
   using C = TmaCfg<P, TPB, R>;
   static int ctas_per_sm[64] = {0};
   if (ctas_per_sm[c->device] == 0)
@@ -1048,18 +1051,18 @@ void launch_apply_tma_t(pmgx_ctx* c, const double* x, double* y, const double* G
   // persistent CTAs: exactly the number that is co-resident, so every SM streams all the time
   const int grid = std::min(nbatch, ctas_per_sm[c->device] * c->num_sms);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (c->profiling)
+  if (timed)
   {
     PMGX_CUDA(cudaEventCreate(&e0));
     PMGX_CUDA(cudaEventCreate(&e1));
-    PMGX_CUDA(cudaEventRecord(e0, c->stream));
+    PMGX_CUDA(cudaEventRecord(e0, st));
   }
-  k_apply_tma<P, TPB, R><<<grid, TPB, C::smem, c->stream>>>(x, y, G, enc, perm, kappa, batch0, cell0, count, nbatch);
+  k_apply_tma<P, TPB, R><<<grid, TPB, C::smem, st>>>(x, y, G, enc, perm, kappa, batch0, cell0, count, nbatch);
   check_launch("k_apply_tma");
   count_launch(c);
-  if (c->profiling)
+  if (timed)
   {
-    PMGX_CUDA(cudaEventRecord(e1, c->stream));
+    PMGX_CUDA(cudaEventRecord(e1, st));
     c->prof[P].emplace_back(e0, e1);
   }
 }
@@ -1070,7 +1073,7 @@ inline int tma_default_tpb(int P) { return (P == 1 || P >= 5) ? 64 : 128; }
 inline int tma_default_r(int P) { return 2; }
 
 template <int P>
-void launch_apply_tma(pmgx_ctx* c, int tpb, int r, const double* x, double* y, const double* G,
+void launch_apply_tma(pmgx_ctx* c, cudaStream_t st, int tpb, int r, const double* x, double* y, const double* G,
                       const int32_t* enc, const int32_t* perm, const double* kappa, long long batch0, int cell0,
                       int count)
 {
@@ -1078,7 +1081,7 @@ void launch_apply_tma(pmgx_ctx* c, int tpb, int r, const double* x, double* y, c
     return;
 #define PMGX_TMA_CASE(T, RR)                                                                       \
   if (tpb == T && r == RR)                                                                         \
-    return launch_apply_tma_t<P, T, RR>(c, x, y, G, enc, perm, kappa, batch0, cell0, count);
+    return launch_apply_tma_t<P, T, RR>(c, st, x, y, G, enc, perm, kappa, batch0, cell0, count);
   PMGX_TMA_CASE(128, 2)
   PMGX_TMA_CASE(128, 3)
   PMGX_TMA_CASE(64, 2)
@@ -1145,29 +1148,33 @@ struct Laplacian : pmgx_operator
     PMGX_CUDA(cudaMemsetAsync(y, 0, (size_t)ntot * sizeof(double), ctx->stream)); // out.set(0) :466
     if (halo)
       halo_fwd_begin(halo, x);                                                    // :378
+    // interior cells on the compute stream; boundary + ghost cells right behind the exchange on
+    // the halo stream: they start when the ghosts are in place and fill the interior kernel's tail
+    // (both only add into y, which was zeroed before the exchange started)
+    cudaStream_t cs = ctx->stream, bs = halo_stream(halo, ctx);
+    bool done = false;
     if constexpr (PP <= SLAB_MAX_DEGREE)
     {
       if (lay.mode == 1 && use_tma)
       {
-        launch_apply_tma<PP>(ctx, tma_tpb, tma_r, x, y, G.p, enc.p, perm.p, kappa, 0, 0, n_l); // :406-409
-        if (halo)
-          halo_fwd_end(halo, x);                                                  // :425
-        launch_apply_tma<PP>(ctx, tma_tpb, tma_r, x, y, G.p, enc.p, perm.p, kappa, lay.nb_l, n_l, n_b); // :449-452
-        return;
+        launch_apply_tma<PP>(ctx, cs, tma_tpb, tma_r, x, y, G.p, enc.p, perm.p, kappa, 0, 0, n_l); // :406-409
+        launch_apply_tma<PP>(ctx, bs, tma_tpb, tma_r, x, y, G.p, enc.p, perm.p, kappa, lay.nb_l, n_l, n_b); // :449-452
+        done = true;
       }
-      if (lay.mode == 1)
+      else if (lay.mode == 1)
       {
-        launch_apply_slab<PP>(ctx, x, y, G.p, enc.p, perm.p, kappa, 0, 0, n_l);
-        if (halo)
-          halo_fwd_end(halo, x);
-        launch_apply_slab<PP>(ctx, x, y, G.p, enc.p, perm.p, kappa, lay.nb_l, n_l, n_b);
-        return;
+        launch_apply_slab<PP>(ctx, cs, x, y, G.p, enc.p, perm.p, kappa, 0, 0, n_l);
+        launch_apply_slab<PP>(ctx, bs, x, y, G.p, enc.p, perm.p, kappa, lay.nb_l, n_l, n_b);
+        done = true;
       }
     }
-    launch_apply<PP>(ctx, x, y, G.p, enc.p, perm.p, kappa, 0, n_l);
+    if (!done)
+    {
+      launch_apply<PP>(ctx, cs, x, y, G.p, enc.p, perm.p, kappa, 0, n_l);
+      launch_apply<PP>(ctx, bs, x, y, G.p, enc.p, perm.p, kappa, n_l, n_b);
+    }
     if (halo)
-      halo_fwd_end(halo, x);
-    launch_apply<PP>(ctx, x, y, G.p, enc.p, perm.p, kappa, n_l, n_b);
+      halo_fwd_end(halo, x);                                                      // :425 (join)
   }
 
   void apply(double* x, double* y) override

@@ -35,6 +35,7 @@ namespace pmgx
 void halo_fwd_begin(pmgx_halo* h, double* x, const double* sub = nullptr);
 void halo_fwd_end(pmgx_halo* h, double* x);
 void halo_setup_p2p(pmgx_halo* h);
+cudaStream_t halo_stream(pmgx_halo* h, pmgx_ctx* c);
 } // namespace pmgx
 
 // Operator concept of the reference (operator()(in,out) + get_diag_inverse,

@@ -10,6 +10,7 @@
 // (exchange of IPC handles) and the fallback when IPC is unavailable (PMGX_P2P=0 forces it).
 #include "common.hpp"
 #include "operator.hpp"
+#include "reduce.cuh"
 
 #include <cstdlib>
 #include <cstring>
@@ -20,51 +21,18 @@ namespace p2p
 {
 namespace
 {
-constexpr int AR_MAX = 4; // operands per all-reduce
-
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
+// Stand-alone all-reduce of device scalars (for reductions whose kernel does not carry the
+// peer epilogue): one CTA running peer_allreduce.
+__global__ void k_allreduce_p2p(PeerReduce pr, double* __restrict__ vals, int count, bool is_max)
 {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
-{
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-
-// One CTA.  Thread r < nranks stores this rank's operands into rank r's slot [buf][myrank] and
-// then releases flag[myrank] = epoch there; it then waits for rank r's operands to arrive here.
-// Thread k < count finally combines the slots in rank order, so every rank gets the same bits.
-__global__ void k_allreduce_p2p(double* const* __restrict__ peers, double* __restrict__ vals, int count,
-                                int myrank, int nranks, unsigned long long epoch, bool is_max)
-{
-  const int r = threadIdx.x;
-  const int buf = (int)(epoch & 1ull);
-  const size_t flag_off = (size_t)2 * nranks * AR_MAX; // in doubles (flags are 8 bytes too)
-  if (r < nranks)
-  {
-    double* dst = peers[r] + ((size_t)buf * nranks + myrank) * AR_MAX;
-    for (int k = 0; k < count; ++k)
-      dst[k] = vals[k];
-    __threadfence_system();
-    st_release_sys(reinterpret_cast<unsigned long long*>(peers[r] + flag_off) + myrank, epoch);
-    const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(peers[myrank] + flag_off) + r;
-    while (ld_acquire_sys(mine) < epoch)
-      __nanosleep(40);
-  }
+  __shared__ double in[AR_MAX];
+  if ((int)threadIdx.x < count)
+    in[threadIdx.x] = vals[threadIdx.x];
   __syncthreads();
-  if (r < count)
-  {
-    const double* src = peers[myrank] + (size_t)buf * nranks * AR_MAX;
-    double acc = __ldcg(src + r);
-    for (int q = 1; q < nranks; ++q)
-    {
-      const double v = __ldcg(src + (size_t)q * AR_MAX + r);
-      acc = is_max ? fmax(acc, v) : acc + v;
-    }
-    vals[r] = acc;
-  }
+  if (is_max)
+    peer_allreduce<true>(pr, in, count, vals);
+  else
+    peer_allreduce<false>(pr, in, count, vals);
 }
 } // namespace
 
@@ -165,6 +133,21 @@ void ctx_teardown(pmgx_ctx* c)
   cudaGetLastError();
 }
 
+// descriptor of the next all-reduce on this context's compute stream (advances the epoch);
+// nranks == 0 when the peer path is off
+PeerReduce next_epoch(pmgx_ctx* c)
+{
+  PeerReduce pr;
+  if (c->p2p)
+  {
+    pr.peers = c->d_ar_peers;
+    pr.myrank = c->rank;
+    pr.nranks = c->nranks;
+    pr.epoch = ++c->ar_epoch;
+  }
+  return pr;
+}
+
 void allreduce(pmgx_ctx* c, int slot, int count, bool is_max)
 {
   if (c->nranks == 1)
@@ -175,9 +158,7 @@ void allreduce(pmgx_ctx* c, int slot, int count, bool is_max)
                             c->comm, c->stream));
     return;
   }
-  ++c->ar_epoch;
-  k_allreduce_p2p<<<1, 32, 0, c->stream>>>(c->d_ar_peers, c->d_scalars + slot, count, c->rank, c->nranks, c->ar_epoch,
-                                           is_max);
+  k_allreduce_p2p<<<1, 32, 0, c->stream>>>(next_epoch(c), c->d_scalars + slot, count, is_max);
   check_launch("k_allreduce_p2p");
   count_launch(c);
 }

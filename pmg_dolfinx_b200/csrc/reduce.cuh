@@ -4,9 +4,77 @@
 #pragma once
 #include <cuda_runtime.h>
 
+struct pmgx_ctx;
+
 namespace pmgx
 {
 constexpr int RED_THREADS = 256;
+constexpr int AR_MAX = 4; // operands per peer-memory all-reduce slot (p2p.cu)
+
+// Cross-GPU epilogue of a grid reduction over NVLink peer memory (p2p.cu): when nranks > 1 the
+// last block does not stop at the local sums but stores them into every peer's slot, releases an
+// epoch flag, waits for the peers' flags and combines the slots in rank order -- the reduction
+// kernel IS the all-reduce, no second launch.  nranks == 0: local reduction only.
+struct PeerReduce
+{
+  double* const* peers = nullptr; // every rank's slot buffer, mapped into this process
+  int myrank = 0, nranks = 0;
+  unsigned long long epoch = 0;
+};
+
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v)
+{
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p)
+{
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// spin until *p >= epoch; a peer that never arrives (crashed rank) traps after ~10 s instead of
+// hanging the GPU
+__device__ __forceinline__ void wait_epoch(const unsigned long long* p, unsigned long long epoch)
+{
+  unsigned int spins = 0;
+  while (ld_acquire_sys_u64(p) < epoch)
+  {
+    __nanosleep(64);
+    if (++spins > (1u << 27))
+      __trap();
+  }
+}
+
+// One CTA: vals[0..count) (shared or global, visible to the CTA) are combined over all ranks and
+// written to out[0..count).  Thread r < nranks talks to rank r.
+template <bool MAX>
+__device__ __forceinline__ void peer_allreduce(const PeerReduce& pr, const double* vals, int count, double* out)
+{
+  const int r = threadIdx.x;
+  const int buf = (int)(pr.epoch & 1ull);
+  const size_t flag_off = (size_t)2 * pr.nranks * AR_MAX; // in 8-byte units
+  if (r < pr.nranks)
+  {
+    double* dst = pr.peers[r] + ((size_t)buf * pr.nranks + pr.myrank) * AR_MAX;
+    for (int k = 0; k < count; ++k)
+      dst[k] = vals[k];
+    __threadfence_system();
+    st_release_sys_u64(reinterpret_cast<unsigned long long*>(pr.peers[r] + flag_off) + pr.myrank, pr.epoch);
+    wait_epoch(reinterpret_cast<const unsigned long long*>(pr.peers[pr.myrank] + flag_off) + r, pr.epoch);
+  }
+  __syncthreads();
+  if (r < count)
+  {
+    const double* src = pr.peers[pr.myrank] + (size_t)buf * pr.nranks * AR_MAX;
+    double acc = __ldcg(src + r);
+    for (int q = 1; q < pr.nranks; ++q)
+    {
+      const double v = __ldcg(src + (size_t)q * AR_MAX + r);
+      acc = MAX ? fmax(acc, v) : acc + v;
+    }
+    out[r] = acc;
+  }
+}
 
 __device__ __forceinline__ double warp_sum(double v)
 {
@@ -31,9 +99,10 @@ __device__ __forceinline__ double warp_max(double v)
 template <int NV, bool MAX = false>
 __device__ __forceinline__ void grid_reduce(double (&v)[NV], double* __restrict__ partials,
                                             unsigned int* __restrict__ counter,
-                                            double* __restrict__ out)
+                                            double* __restrict__ out, const PeerReduce pr = PeerReduce())
 {
   __shared__ double sh[NV][RED_THREADS / 32];
+  __shared__ double res[NV];
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -88,10 +157,26 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], double* __restrict_
       double w = lane < RED_THREADS / 32 ? sh[k][lane] : (MAX ? -1.0 : 0.0);
       w = MAX ? warp_max(w) : warp_sum(w);
       if (lane == 0)
-        out[k] = w;
+      {
+        if (pr.nranks > 1)
+          res[k] = w;
+        else
+          out[k] = w;
+      }
     }
     if (lane == 0)
       *counter = 0u;
   }
+  if (pr.nranks > 1)
+  {
+    __syncthreads();
+    peer_allreduce<MAX>(pr, res, NV, out);
+  }
 }
+namespace p2p
+{
+// descriptor of the next all-reduce on the context's compute stream (advances the epoch);
+// nranks == 0 when the peer-memory path is off (single rank or NCCL fallback)
+PeerReduce next_epoch(pmgx_ctx* c);
+} // namespace p2p
 } // namespace pmgx

@@ -231,7 +231,7 @@ k_cgcg_update(const double* __restrict__ sc_cur, const double* __restrict__ sc_o
 // out[0] = r.u, out[1] = w.u
 __global__ void __launch_bounds__(FT)
 k_dot2(const double* __restrict__ r, const double* __restrict__ w, const double* __restrict__ u, long long n,
-       double* partials, unsigned int* counter, double* out)
+       double* partials, unsigned int* counter, double* out, const PeerReduce pr)
 {
   const long long nth = (long long)gridDim.x * blockDim.x;
   double a = 0.0, b = 0.0;
@@ -242,7 +242,7 @@ k_dot2(const double* __restrict__ r, const double* __restrict__ w, const double*
     b = fma(w[i], uv, b);
   }
   double v[2] = {a, b};
-  grid_reduce<2>(v, partials, counter, out);
+  grid_reduce<2>(v, partials, counter, out, pr); // the last block is also the all-reduce over ranks
 }
 
 void check(const char* w) { check_launch(w); }
@@ -456,10 +456,12 @@ int cgcg_solve(pmgx_cg* s, pmgx_operator* A, double* x, const double* b, int che
   auto spmv_dots = [&](double* out2, int slot)
   {
     A->apply(s->u.p, w);
-    k_dot2<<<grid, FT, 0, c->stream>>>(s->r.p, w, s->u.p, n, c->d_partials, c->d_counter, out2);
+    const PeerReduce pr = p2p::next_epoch(c);
+    k_dot2<<<grid, FT, 0, c->stream>>>(s->r.p, w, s->u.p, n, c->d_partials, c->d_counter, out2, pr);
     check("k_dot2");
     count_launch(c);
-    vec::allreduce_scalars(c, slot, 2, false);
+    if (pr.nranks == 0)
+      vec::allreduce_scalars(c, slot, 2, false); // NCCL (no-op on one rank)
   };
   if (!x_is_zero)
     A->apply(x, w);
