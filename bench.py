@@ -321,12 +321,13 @@ def run_gpu(args):
     bb = [b, api.Vector(ctx, sp.n_owned, sp.n_ghost, halo_top)]
     us = [torch.empty(n_owned, dtype=torch.float64, device=ctx.device) for _ in range(2)]
     s_up, s_down = torch.cuda.Stream(device=ctx.device), torch.cuda.Stream(device=ctx.device)
-    e2e_steps = max(4, args.steps)
+    e2e_steps = max(2, args.steps)
 
     def e2e_loop(nsteps, e_begin=None, e_end=None):
-        up = [torch.cuda.Event() for _ in range(nsteps)]      # b of step i is on the device
-        used = [torch.cuda.Event() for _ in range(nsteps)]    # V-cycle i has consumed its b, u snapshot taken
-        down = [torch.cuda.Event() for _ in range(nsteps)]    # u of step i is on the host
+        trace = bool(os.environ.get("PMGX_E2E_TRACE")) and e_begin is not None
+        up = [torch.cuda.Event(enable_timing=trace) for _ in range(nsteps)]      # b of step i is on the device
+        used = [torch.cuda.Event(enable_timing=trace) for _ in range(nsteps)]    # V-cycle i done with b, u snapshot taken
+        down = [torch.cuda.Event(enable_timing=trace) for _ in range(nsteps)]    # u of step i is on the host
         if e_begin is not None:
             e_begin.record(ctx.stream)
         s_up.wait_stream(ctx.stream)
@@ -357,12 +358,30 @@ def run_gpu(args):
             ctx.stream.wait_event(down[-2])
         if e_end is not None:
             e_end.record(ctx.stream)
+        if trace and rank == 0:
+            ctx.sync()
+            torch.cuda.synchronize()
+            for i in range(nsteps):
+                sys.stderr.write(f"e2e step {i}: b on device {e_begin.elapsed_time(up[i]):8.2f}  cycle done "
+                                 f"{e_begin.elapsed_time(used[i]):8.2f}  u on host {e_begin.elapsed_time(down[i]):8.2f} ms\n")
 
-    e2e_loop(2)
+    # same cycles as the device-resident measurement: restart from u = 0, W untimed cycles, K timed
+    # (the cost of a cycle depends on how far the solve has converged: the coarse PCG stops early
+    # on the first cycles and runs into its 60-iteration cap later)
+    u.set(0.0)
+    e2e_loop(max(args.warmup, 2))
     barrier()
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if os.environ.get("PMGX_E2E_TRACE"):
+        api.check(api.lib.pmgx_ctx_profile(ctx.h, 1))
     e2e_loop(e2e_steps, s0, s1)
     barrier()
+    if os.environ.get("PMGX_E2E_TRACE"):
+        tms, tl = ctypes.c_double(), ctypes.c_longlong()
+        api.check(api.lib.pmgx_ctx_profile_read(ctx.h, Ptop, ctypes.addressof(tms), ctypes.addressof(tl)))
+        api.check(api.lib.pmgx_ctx_profile(ctx.h, 0))
+        if rank == 0:
+            sys.stderr.write(f"e2e: P{Ptop} apply launches {tl.value}, avg {tms.value / max(tl.value, 1):.3f} ms\n")
     te = torch.tensor([s0.elapsed_time(s1) / e2e_steps], dtype=torch.float64, device=ctx.device)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)

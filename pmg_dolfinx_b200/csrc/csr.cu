@@ -114,7 +114,7 @@ void CsrOperator::apply(double* x, double* y)
   const int grid = (int)(((long long)n_owned * LPR + ST - 1) / ST);
   // ghost entries of y are zeroed like y.set(0) (src/csr.hpp:225)
   if (n_ghost > 0)
-    PMGX_CUDA(cudaMemsetAsync(y + n_owned, 0, (size_t)n_ghost * sizeof(double), ctx->stream));
+    vec::set(ctx, y + n_owned, n_ghost, 0.0);
   if (halo)
     halo_fwd_begin(halo, x);                                                       // :255
   if (n_owned > 0)

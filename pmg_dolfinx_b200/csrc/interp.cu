@@ -383,7 +383,7 @@ void interp_restrict(pmgx_interp* it, double* fine, const double* sub, double* c
 {
   pmgx_ctx* c = it->ctx;
   PMGX_CUDA(cudaSetDevice(c->device));
-  PMGX_CUDA(cudaMemsetAsync(coarse, 0, (size_t)it->n_coarse_total * sizeof(double), c->stream));
+  vec::set(c, coarse, it->n_coarse_total, 0.0);
   if (it->halo_f)
     halo_fwd_begin(it->halo_f, fine, sub);                                           // :264
   cudaStream_t bs = halo_stream(it->halo_f, c);

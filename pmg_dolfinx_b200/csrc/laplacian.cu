@@ -1145,7 +1145,7 @@ struct Laplacian : pmgx_operator
   void apply_t(double* x, double* y)
   {
     const long long ntot = (long long)n_owned + n_ghost;
-    PMGX_CUDA(cudaMemsetAsync(y, 0, (size_t)ntot * sizeof(double), ctx->stream)); // out.set(0) :466
+    vec::set(ctx, y, ntot, 0.0); // out.set(0) :466 (fill kernel, see vec::set)
     if (halo)
       halo_fwd_begin(halo, x);                                                    // :378
     // interior cells on the compute stream; boundary + ghost cells right behind the exchange on

@@ -11,6 +11,7 @@
 #include "reduce.cuh"
 
 #include <cmath>
+#include <cstdlib>
 
 namespace pmgx
 {
@@ -404,9 +405,7 @@ int cg_solve(pmgx_cg* s, pmgx_operator* A, double* x, const double* b)
     count_launch(c);
     vec::allreduce_scalars(c, 3, 1, false);
     // one host round trip per iteration: p.y (for alpha) and the new r.M^-1 r
-    PMGX_CUDA(cudaMemcpyAsync(c->h_scalars + 2, c->d_scalars + 2, 2 * sizeof(double),
-                              cudaMemcpyDeviceToHost, c->stream));
-    PMGX_CUDA(cudaStreamSynchronize(c->stream));
+    vec::publish_scalars(c, 2, 2);
     const double alpha = rnorm / c->h_scalars[2];
     const double rnorm_new = c->h_scalars[3];
     const double beta = rnorm_new / rnorm;
@@ -487,9 +486,7 @@ int cgcg_solve(pmgx_cg* s, pmgx_operator* A, double* x, const double* b, int che
     if (k % check_every == 0)
     {
       // the only host round trips of the solve: gamma slots 16..19, alpha 20..21, gamma0 22
-      PMGX_CUDA(cudaMemcpyAsync(c->h_scalars + 16, c->d_scalars + 16, 7 * sizeof(double), cudaMemcpyDeviceToHost,
-                                c->stream));
-      PMGX_CUDA(cudaStreamSynchronize(c->stream));
+      vec::publish_scalars(c, 16, 7);
       const double r = c->h_scalars[16 + 2 * nxt];
       s->rnorm0 = c->h_scalars[22];
       s->history.push_back(r);
@@ -879,7 +876,8 @@ int pmgx_vcycle_apply(pmgx_vcycle* v, const double* b_in, double* u_inout, doubl
   const pmgx::ChebResidual post = literal_seq ? pmgx::CHEB_R_FULL : pmgx::CHEB_R_NONE;
   if (v->coarse && nl > 1)
   {
-    v->coarse->last_iters = pmgx::cgcg_solve(v->coarse->cg, v->coarse->A, U[0], B[0], 8, true); // :106-107 (u[0] = 0)
+    static const int every = getenv("PMGX_COARSE_CHECK_EVERY") ? atoi(getenv("PMGX_COARSE_CHECK_EVERY")) : 8;
+    v->coarse->last_iters = pmgx::cgcg_solve(v->coarse->cg, v->coarse->A, U[0], B[0], every, true); // :106-107 (u[0] = 0)
   }
   else
     pmgx::cheb_solve(v->smoothers[0], v->ops[0], U[0], B[0], nullptr, !literal_seq && nl > 1, post); // :109
