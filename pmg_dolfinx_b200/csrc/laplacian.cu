@@ -1151,19 +1151,31 @@ struct Laplacian : pmgx_operator
     // interior cells on the compute stream; boundary + ghost cells right behind the exchange on
     // the halo stream: they start when the ghosts are in place and fill the interior kernel's tail
     // (both only add into y, which was zeroed before the exchange started)
-    cudaStream_t cs = ctx->stream, bs = halo_stream(halo, ctx);
+    static const bool on_compute = getenv("PMGX_BOUNDARY_ON_COMPUTE") != nullptr; // A/B switch
+    // measured at 4 GPUs (scripts/ab_apply_mgpu.py): riding the halo stream wins at P1 (0.114 vs
+    // 0.121 ms), is neutral at P2 and loses 2 % at P4, where the interior kernel is long enough to
+    // hide the join anyway
+    const bool side = halo && !on_compute && PP <= 2;
+    cudaStream_t cs = ctx->stream, bs = side ? halo_stream(halo, ctx) : ctx->stream;
+    auto join_before_boundary = [&]()
+    {
+      if (halo && !side)
+        halo_fwd_end(halo, x); // reference order: wait for the ghosts, then the boundary launch (:425)
+    };
     bool done = false;
     if constexpr (PP <= SLAB_MAX_DEGREE)
     {
       if (lay.mode == 1 && use_tma)
       {
         launch_apply_tma<PP>(ctx, cs, tma_tpb, tma_r, x, y, G.p, enc.p, perm.p, kappa, 0, 0, n_l); // :406-409
+        join_before_boundary();
         launch_apply_tma<PP>(ctx, bs, tma_tpb, tma_r, x, y, G.p, enc.p, perm.p, kappa, lay.nb_l, n_l, n_b); // :449-452
         done = true;
       }
       else if (lay.mode == 1)
       {
         launch_apply_slab<PP>(ctx, cs, x, y, G.p, enc.p, perm.p, kappa, 0, 0, n_l);
+        join_before_boundary();
         launch_apply_slab<PP>(ctx, bs, x, y, G.p, enc.p, perm.p, kappa, lay.nb_l, n_l, n_b);
         done = true;
       }
@@ -1171,9 +1183,10 @@ struct Laplacian : pmgx_operator
     if (!done)
     {
       launch_apply<PP>(ctx, cs, x, y, G.p, enc.p, perm.p, kappa, 0, n_l);
+      join_before_boundary();
       launch_apply<PP>(ctx, bs, x, y, G.p, enc.p, perm.p, kappa, n_l, n_b);
     }
-    if (halo)
+    if (side)
       halo_fwd_end(halo, x);                                                      // :425 (join)
   }
 
