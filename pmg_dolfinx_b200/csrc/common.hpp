@@ -137,7 +137,7 @@ struct pmgx_ctx
   double* ar_local = nullptr;             // [2][nranks][4] operands + nranks uint64 epoch flags
   double** d_ar_peers = nullptr;          // device array [nranks]: every rank's ar_local, mapped here
   std::vector<void*> p2p_mapped;          // IPC mappings to close at destroy
-  unsigned long long ar_epoch = 0;
+  unsigned long long* d_ar_epoch = nullptr; // device counter of completed all-reduces
   long long launches = 0;
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[PMGX_MAX_DEGREE + 1];

@@ -3,6 +3,7 @@
 // (examples/pmg/select_gpu.sh, src/vector.hpp:350) by an explicit per-GPU context.
 #include "common.hpp"
 
+#include <cstdlib>
 #include <cstring>
 
 extern "C"

@@ -52,9 +52,10 @@ __global__ void __launch_bounds__(PT)
 k_pack_p2p(int ns, int n_nbr, const int* __restrict__ send_offsets, const int32_t* __restrict__ idx,
            const double* __restrict__ x, const double* __restrict__ sub, double* const* __restrict__ peer_dst,
            const long long* __restrict__ peer_stride, unsigned long long* const* __restrict__ peer_flag,
-           unsigned long long epoch, unsigned int* ticket)
+           unsigned long long* __restrict__ epoch_ptr, unsigned int* ticket)
 {
   __shared__ bool is_last;
+  const unsigned long long epoch = *epoch_ptr + 1; // stored back by the last CTA, after every CTA's ticket
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < ns)
   {
@@ -76,22 +77,28 @@ k_pack_p2p(int ns, int n_nbr, const int* __restrict__ send_offsets, const int32_
   if ((int)threadIdx.x < n_nbr)
     st_release_sys_u64(peer_flag[threadIdx.x], epoch);
   if (threadIdx.x == 0)
+  {
     *ticket = 0u;
+    *epoch_ptr = epoch;
+  }
 }
 
 // One small CTA that waits until every source rank has released this epoch; the unpack kernel
 // behind it in the stream then only runs once the data is here (no spinning CTAs holding SMs
 // that the interior-cell kernel wants).
-__global__ void k_wait_p2p(int n_nbr, const unsigned long long* __restrict__ flags, unsigned long long epoch)
+__global__ void k_wait_p2p(int n_nbr, const unsigned long long* __restrict__ flags,
+                           const unsigned long long* __restrict__ epoch_ptr)
 {
+  const unsigned long long epoch = *epoch_ptr; // the pack kernel before this one has advanced it
   for (int t = threadIdx.x; t < n_nbr; t += blockDim.x)
     wait_epoch(flags + t, epoch); // traps after ~10 s if a neighbour never arrives
 }
 
-__global__ void k_unpack_cg(int n, const int32_t* __restrict__ idx, const double* __restrict__ in,
-                            double* __restrict__ out)
+__global__ void k_unpack_cg(int n, const int32_t* __restrict__ idx, const double* __restrict__ bufs,
+                            const unsigned long long* __restrict__ epoch_ptr, double* __restrict__ out)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const double* in = bufs + (*epoch_ptr & 1ull) * (size_t)n; // receive buffer of this epoch's parity
   if (i < n)
     out[idx[i]] = __ldcg(in + i); // written by a remote GPU: bypass L1
 }
@@ -110,21 +117,19 @@ static void halo_fwd_begin_p2p(pmgx_halo* h, double* x, const double* sub)
 {
   pmgx_ctx* c = h->ctx;
   const int ns = h->n_send(), nr = h->n_recv();
-  ++h->epoch;
   if (ns > 0)
   {
     k_pack_p2p<<<(ns + PT - 1) / PT, PT, 0, c->comm_stream>>>(ns, (int)h->send_ranks.size(), h->d_send_offsets.p,
                                                              h->send_idx.p, x, sub, h->d_peer_dst.p, h->d_peer_stride.p,
-                                                             h->d_peer_flag.p, h->epoch, h->d_ticket.p);
+                                                             h->d_peer_flag.p, h->d_epoch.p, h->d_ticket.p);
     check_launch("k_pack_p2p");
     count_launch(c);
   }
   if (nr > 0)
   {
     const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(h->xbuf + 2 * (size_t)std::max(nr, 1));
-    k_wait_p2p<<<1, 32, 0, c->comm_stream>>>((int)h->recv_ranks.size(), flags, h->epoch);
-    k_unpack_cg<<<(nr + PT - 1) / PT, PT, 0, c->comm_stream>>>(nr, h->recv_idx.p, h->xbuf + (h->epoch & 1ull) * (size_t)nr,
-                                                              x + h->n_owned);
+    k_wait_p2p<<<1, 32, 0, c->comm_stream>>>((int)h->recv_ranks.size(), flags, h->d_epoch.p);
+    k_unpack_cg<<<(nr + PT - 1) / PT, PT, 0, c->comm_stream>>>(nr, h->recv_idx.p, h->xbuf, h->d_epoch.p, x + h->n_owned);
     check_launch("k_unpack(p2p)");
     count_launch(c, 2);
   }
@@ -268,7 +273,9 @@ void halo_setup_p2p(pmgx_halo* h)
   h->d_peer_flag.upload(flag.data(), nn, c->stream);
   h->d_send_offsets.upload(h->send_offsets.data(), h->send_offsets.size(), c->stream);
   h->d_ticket.alloc(1);
+  h->d_epoch.alloc(1);
   PMGX_CUDA(cudaMemsetAsync(h->d_ticket.p, 0, sizeof(unsigned int), c->stream));
+  PMGX_CUDA(cudaMemsetAsync(h->d_epoch.p, 0, sizeof(unsigned long long), c->stream));
   PMGX_CUDA(cudaStreamSynchronize(c->stream));
   h->p2p = true;
 }

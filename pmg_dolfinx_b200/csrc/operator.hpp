@@ -24,7 +24,7 @@ struct pmgx_halo
   pmgx::DevBuf<int> d_send_offsets;              // n_send_nbr + 1
   pmgx::DevBuf<unsigned int> d_ticket;
   std::vector<void*> mapped;
-  unsigned long long epoch = 0;
+  pmgx::DevBuf<unsigned long long> d_epoch;      // completed exchanges (device-resident: launches carry no per-call state)
   int n_send() const { return send_offsets.empty() ? 0 : send_offsets.back(); }
   int n_recv() const { return recv_offsets.empty() ? 0 : recv_offsets.back(); }
 };

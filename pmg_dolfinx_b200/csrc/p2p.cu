@@ -113,6 +113,8 @@ void ctx_setup(pmgx_ctx* c)
     ctx_teardown(c);
     return;
   }
+  PMGX_CUDA(cudaMalloc(&c->d_ar_epoch, sizeof(unsigned long long)));
+  PMGX_CUDA(cudaMemset(c->d_ar_epoch, 0, sizeof(unsigned long long)));
   PMGX_CUDA(cudaMalloc(&c->d_ar_peers, c->nranks * sizeof(double*)));
   PMGX_CUDA(cudaMemcpy(c->d_ar_peers, peers.data(), c->nranks * sizeof(double*), cudaMemcpyHostToDevice));
   c->p2p = true;
@@ -127,13 +129,16 @@ void ctx_teardown(pmgx_ctx* c)
     cudaFree(c->ar_local);
   if (c->d_ar_peers)
     cudaFree(c->d_ar_peers);
+  if (c->d_ar_epoch)
+    cudaFree(c->d_ar_epoch);
+  c->d_ar_epoch = nullptr;
   c->ar_local = nullptr;
   c->d_ar_peers = nullptr;
   c->p2p = false;
   cudaGetLastError();
 }
 
-// descriptor of the next all-reduce on this context's compute stream (advances the epoch);
+// descriptor of an all-reduce on this context's compute stream (the epoch lives on the device);
 // nranks == 0 when the peer path is off
 PeerReduce next_epoch(pmgx_ctx* c)
 {
@@ -143,7 +148,7 @@ PeerReduce next_epoch(pmgx_ctx* c)
     pr.peers = c->d_ar_peers;
     pr.myrank = c->rank;
     pr.nranks = c->nranks;
-    pr.epoch = ++c->ar_epoch;
+    pr.epoch_ptr = c->d_ar_epoch;
   }
   return pr;
 }

@@ -19,7 +19,9 @@ struct PeerReduce
 {
   double* const* peers = nullptr; // every rank's slot buffer, mapped into this process
   int myrank = 0, nranks = 0;
-  unsigned long long epoch = 0;
+  // device counter of completed all-reduces: the kernel takes *epoch_ptr + 1 and stores it back,
+  // so a launch carries no per-call state and can be replayed from a CUDA graph
+  unsigned long long* epoch_ptr = nullptr;
 };
 
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v)
@@ -51,7 +53,8 @@ template <bool MAX>
 __device__ __forceinline__ void peer_allreduce(const PeerReduce& pr, const double* vals, int count, double* out)
 {
   const int r = threadIdx.x;
-  const int buf = (int)(pr.epoch & 1ull);
+  const unsigned long long epoch = *pr.epoch_ptr + 1; // read by every thread before anyone stores it back
+  const int buf = (int)(epoch & 1ull);
   const size_t flag_off = (size_t)2 * pr.nranks * AR_MAX; // in 8-byte units
   if (r < pr.nranks)
   {
@@ -59,8 +62,8 @@ __device__ __forceinline__ void peer_allreduce(const PeerReduce& pr, const doubl
     for (int k = 0; k < count; ++k)
       dst[k] = vals[k];
     __threadfence_system();
-    st_release_sys_u64(reinterpret_cast<unsigned long long*>(pr.peers[r] + flag_off) + pr.myrank, pr.epoch);
-    wait_epoch(reinterpret_cast<const unsigned long long*>(pr.peers[pr.myrank] + flag_off) + r, pr.epoch);
+    st_release_sys_u64(reinterpret_cast<unsigned long long*>(pr.peers[r] + flag_off) + pr.myrank, epoch);
+    wait_epoch(reinterpret_cast<const unsigned long long*>(pr.peers[pr.myrank] + flag_off) + r, epoch);
   }
   __syncthreads();
   if (r < count)
@@ -74,6 +77,8 @@ __device__ __forceinline__ void peer_allreduce(const PeerReduce& pr, const doubl
     }
     out[r] = acc;
   }
+  if (r == 0)
+    *pr.epoch_ptr = epoch; // after the barrier above: every thread of the CTA has read the old value
 }
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -175,7 +180,7 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], double* __restrict_
 }
 namespace p2p
 {
-// descriptor of the next all-reduce on the context's compute stream (advances the epoch);
+// descriptor of an all-reduce on the context's compute stream;
 // nranks == 0 when the peer-memory path is off (single rank or NCCL fallback)
 PeerReduce next_epoch(pmgx_ctx* c);
 } // namespace p2p

@@ -12,6 +12,7 @@
 
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 namespace pmgx
 {
@@ -368,7 +369,14 @@ struct pmgx_cg
   double rtol = 0.0;
   bool store = false;
   pmgx::DevBuf<double> r, y, p; // src/cg.hpp:241-244
-  pmgx::DevBuf<double> u, s2;   // extra work vectors of the single-reduction coarse variant (lazy)
+  pmgx::DevBuf<double> slab;    // r, w, p, u, s of the single-reduction coarse variant, contiguous (lazy)
+  // CUDA graph of one block of `graph_len` coarse iterations (captured from the stream on first use,
+  // replayed between the host's convergence checks): the ~8 small launches and 4 cross-stream
+  // events of an iteration cost more in launch gaps than the kernels of a 1.6 M-dof level run
+  cudaGraphExec_t graph = nullptr;
+  const void* graph_key[3] = {nullptr, nullptr, nullptr}; // operator, x, block length
+  int graph_launches = 0;
+  bool graph_off = false;
   std::vector<double> alphas, betas, residuals; // stored coefficients (:213-218)
   std::vector<double> history;                  // every iteration's r.M^-1 r
   double rnorm0 = 0.0;
@@ -439,24 +447,34 @@ int cgcg_solve(pmgx_cg* s, pmgx_operator* A, double* x, const double* b, int che
   const double* dinv = A->diag_inv.p;
   const int grid = fused_grid(c, n);
   const size_t nt = (size_t)s->n_owned + s->n_ghost;
-  if (s->u.n != nt)
+  // the five work vectors live in one slab
+  const size_t ntp = (nt + 15) & ~(size_t)15;
+  if (s->slab.n != 5 * ntp)
   {
-    s->u.alloc(nt);
-    s->s2.alloc(nt);
+    s->slab.alloc(5 * ntp);
     if (nt > 0)
+      PMGX_CUDA(cudaMemsetAsync(s->slab.p, 0, 5 * ntp * sizeof(double), c->stream));
+    if (s->graph)
     {
-      PMGX_CUDA(cudaMemsetAsync(s->u.p, 0, nt * sizeof(double), c->stream));
-      PMGX_CUDA(cudaMemsetAsync(s->s2.p, 0, nt * sizeof(double), c->stream));
+      cudaGraphExecDestroy(s->graph);
+      s->graph = nullptr;
     }
   }
+  double* const cr = s->slab.p;            // r
+  double* const w = s->slab.p + ntp;       // w = A u
+  double* const cp = s->slab.p + 2 * ntp;  // p
+  double* const cu = s->slab.p + 3 * ntp;  // u = D^-1 r
+  double* const cs = s->slab.p + 4 * ntp;  // s = A p
+  // (An L2 access-policy window that pins this slab in a persisting set-aside was measured: the
+  // coarse solve gains 4 %, but the set-aside costs the fine-level kernels their L2 and the whole
+  // V-cycle goes from 22 to 31 ms -- not used.)
   double* sc = c->d_scalars + 16;  // sc[2*(it&1) + {0,1}] = {gamma, delta}
   double* al = c->d_scalars + 20;  // al[it&1] = alpha
-  double* w = s->y.p;
   auto spmv_dots = [&](double* out2, int slot)
   {
-    A->apply(s->u.p, w);
+    A->apply(cu, w);
     const PeerReduce pr = p2p::next_epoch(c);
-    k_dot2<<<grid, FT, 0, c->stream>>>(s->r.p, w, s->u.p, n, c->d_partials, c->d_counter, out2, pr);
+    k_dot2<<<grid, FT, 0, c->stream>>>(cr, w, cu, n, c->d_partials, c->d_counter, out2, pr);
     check("k_dot2");
     count_launch(c);
     if (pr.nranks == 0)
@@ -464,25 +482,91 @@ int cgcg_solve(pmgx_cg* s, pmgx_operator* A, double* x, const double* b, int che
   };
   if (!x_is_zero)
     A->apply(x, w);
-  k_cgcg_init<<<grid, FT, 0, c->stream>>>(b, x_is_zero ? nullptr : w, dinv, s->r.p, s->u.p, x, x_is_zero, n);
+  k_cgcg_init<<<grid, FT, 0, c->stream>>>(b, x_is_zero ? nullptr : w, dinv, cr, cu, x, x_is_zero, n);
   check("k_cgcg_init");
   count_launch(c);
   spmv_dots(sc, 16);
   s->history.clear();
   const double rtol2 = s->rtol * s->rtol;
   double* g0 = c->d_scalars + 22; // gamma of iteration 0, next to the ping-pong slots: one D2H reads both
-  int k = 0;
-  while (k < s->max_iter)
+  // one full iteration: vector update with the scalars of slot k&1, then SpMV + inner products
+  // into the other slot
+  auto iterate = [&](int k)
   {
     const int cur = k & 1, nxt = cur ^ 1;
     k_cgcg_update<<<grid, FT, 0, c->stream>>>(sc + 2 * cur, sc + 2 * nxt, al + nxt, al + cur, g0, k == 0, dinv, w,
-                                              s->p.p, s->s2.p, x, s->r.p, s->u.p, n);
+                                              cp, cs, x, cr, cu, n);
     check("k_cgcg_update");
     count_launch(c);
-    ++k;
-    if (k == s->max_iter)
-      break;
-    spmv_dots(sc + 2 * nxt, 16 + 2 * nxt);
+    if (k + 1 < s->max_iter)
+      spmv_dots(sc + 2 * nxt, 16 + 2 * nxt);
+  };
+  // blocks [k0, k0 + check_every) with k0 even, k0 >= 2 and no last iteration inside are identical
+  // launch sequences: capture once, replay
+  static const bool graphs_enabled = !(getenv("PMGX_COARSE_GRAPH") && atoi(getenv("PMGX_COARSE_GRAPH")) == 0);
+  const bool block_ok = graphs_enabled && !s->graph_off && check_every >= 2 && check_every % 2 == 0;
+  auto run_block = [&](int k0)
+  {
+    const void* key[3] = {A, x, reinterpret_cast<const void*>((size_t)check_every)};
+    if (s->graph && (s->graph_key[0] != key[0] || s->graph_key[1] != key[1] || s->graph_key[2] != key[2]))
+    {
+      cudaGraphExecDestroy(s->graph);
+      s->graph = nullptr;
+    }
+    if (!s->graph)
+    {
+      const long long l0 = c->launches;
+      cudaGraph_t g = nullptr;
+      bool ok = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+      if (ok)
+      {
+        try
+        {
+          for (int k = k0; k < k0 + check_every; ++k)
+            iterate(k);
+        }
+        catch (const Error&)
+        {
+          ok = false;
+        }
+        ok = (cudaStreamEndCapture(c->stream, &g) == cudaSuccess) && ok && g != nullptr;
+      }
+      if (ok)
+        ok = cudaGraphInstantiate(&s->graph, g, 0) == cudaSuccess;
+      if (g)
+        cudaGraphDestroy(g);
+      s->graph_launches = (int)(c->launches - l0);
+      c->launches = l0;
+      if (!ok)
+      {
+        cudaGetLastError();
+        s->graph = nullptr;
+        s->graph_off = true; // this configuration cannot be captured: plain launches from now on
+        for (int k = k0; k < k0 + check_every; ++k)
+          iterate(k);
+        return;
+      }
+      s->graph_key[0] = key[0], s->graph_key[1] = key[1], s->graph_key[2] = key[2];
+    }
+    PMGX_CUDA(cudaGraphLaunch(s->graph, c->stream));
+    count_launch(c, s->graph_launches);
+  };
+  int k = 0;
+  while (k < s->max_iter)
+  {
+    if (block_ok && k >= 2 && k % check_every == 0 && k + check_every < s->max_iter && !s->graph_off)
+    {
+      run_block(k);
+      k += check_every;
+    }
+    else
+    {
+      iterate(k);
+      ++k;
+      if (k == s->max_iter)
+        break;
+    }
+    const int nxt = k & 1; // slot written by the last spmv_dots
     if (k % check_every == 0)
     {
       // the only host round trips of the solve: gamma slots 16..19, alpha 20..21, gamma0 22
@@ -711,6 +795,8 @@ int pmgx_cg_destroy(pmgx_cg* s)
   {
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
+    if (s->graph)
+      cudaGraphExecDestroy(s->graph);
     delete s;
   }
   PMGX_API_END
@@ -730,6 +816,9 @@ int pmgx_coarse_create(pmgx_ctx* ctx, pmgx_operator* A, int max_iter, double rto
   cs->cg->max_iter = max_iter;
   cs->cg->rtol = rtol;
   cs->cg->store = false;
+  cs->cg->r.release(); // the coarse variant works in its own slab
+  cs->cg->y.release();
+  cs->cg->p.release();
   *out = cs.release();
   PMGX_API_END
 }
