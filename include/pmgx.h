@@ -137,6 +137,9 @@ int pmgx_vec_norm(pmgx_ctx* ctx, const double* a, long long n, int linf, double*
 #define PMGX_LAP_DEFAULT 0
 #define PMGX_LAP_LITERAL_DETJ 1   /* reproduce detJ of src/laplacian.hpp:97 verbatim (quirk Q17) */
 #define PMGX_LAP_NO_DIAG 2        /* skip the matrix-free diagonal at create */
+#define PMGX_LAP_STREAM_G 4       /* always stream the per-quadrature-point G (the reference's data flow,
+                                     src/laplacian.hpp:221-227); default: when every cell of the operator is
+                                     affine the apply uses one geometry 6-vector per cell, G(q) = w_q Gc */
 
 /* MatFreeLaplacian ctor (src/laplacian.hpp:289-349).  dofmap[n_cells][(P+1)^3],
  * xgeom[n_points][3], geom_dofmap[n_cells][8] (tensor-product vertex order),
@@ -155,6 +158,8 @@ int pmgx_laplacian_create(pmgx_ctx* ctx, int degree, int n_cells, const int32_t*
 /* Geometry factors in the reference layout G[n_list][nq][6] (src/laplacian.hpp:99-111), list
  * order = lcells then bcells (:329-336); for parity tests against geometry_computation. */
 int pmgx_laplacian_get_G(pmgx_operator* op, double* G_out);
+/* 1 when the operator runs the affine-geometry kernel (all cells affine, no PMGX_LAP_STREAM_G) */
+int pmgx_laplacian_is_affine(pmgx_operator* op);
 
 /* ------------------------------------------------------------- CSR operator -- */
 /* MatrixOperator (src/csr.hpp:57-131): row_ptr[n_rows+1], off_diag_offset[n_rows] (first

@@ -165,6 +165,71 @@ __global__ void k_geometry(int P, const double* __restrict__ xgeom,
   }
 }
 
+// Per cell: Gc = K K^T / det J of the trilinear map at the cell centre (weight 1), and the affinity
+// test: a cell is affine iff every vertex equals v000 + a e1 + b e2 + c e3; the deviation is
+// measured against the longest edge.  One thread per launch position.
+__global__ void k_cell_geometry(const double* __restrict__ xgeom, const int32_t* __restrict__ geom_dofmap,
+                                const int32_t* __restrict__ perm, double* __restrict__ Gc, int n_list,
+                                bool literal_detj, double tol, int* __restrict__ n_nonaffine)
+{
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_list)
+    return;
+  const int32_t* gd = geom_dofmap + (long long)perm[p] * 8;
+  double v[8][3];
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      v[k][i] = xgeom[3ll * gd[k] + i];
+  // tensor-product vertex order: k = 4a + 2b + c (src/mesh.hpp:75-84)
+  double scale = 0.0, dev = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+  {
+    const double e1 = v[4][i] - v[0][i], e2 = v[2][i] - v[0][i], e3 = v[1][i] - v[0][i];
+    scale = fmax(scale, fmax(fabs(e1), fmax(fabs(e2), fabs(e3))));
+    dev = fmax(dev, fabs(v[6][i] - (v[0][i] + e1 + e2)));
+    dev = fmax(dev, fabs(v[5][i] - (v[0][i] + e1 + e3)));
+    dev = fmax(dev, fabs(v[3][i] - (v[0][i] + e2 + e3)));
+    dev = fmax(dev, fabs(v[7][i] - (v[0][i] + e1 + e2 + e3)));
+  }
+  if (!(dev <= tol * scale))
+    atomicAdd(n_nonaffine, 1);
+  double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+  {
+    const int a = (k >> 2) & 1, b = (k >> 1) & 1, c = k & 1;
+    const double dphi[3] = {(a ? 1.0 : -1.0) * 0.25, (b ? 1.0 : -1.0) * 0.25, (c ? 1.0 : -1.0) * 0.25};
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        J[i][j] += v[k][i] * dphi[j];
+  }
+  double K[3][3];
+  K[0][0] = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+  K[0][1] = -J[0][1] * J[2][2] + J[0][2] * J[2][1];
+  K[0][2] = J[0][1] * J[1][2] - J[0][2] * J[1][1];
+  K[1][0] = -J[1][0] * J[2][2] + J[1][2] * J[2][0];
+  K[1][1] = J[0][0] * J[2][2] - J[0][2] * J[2][0];
+  K[1][2] = -J[0][0] * J[1][2] + J[0][2] * J[1][0];
+  K[2][0] = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+  K[2][1] = -J[0][0] * J[2][1] + J[0][1] * J[2][0];
+  K[2][2] = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+  const double detJ = literal_detj ? J[0][0] * K[0][0] - J[1][0] * K[0][1] + J[0][2] * K[2][0]
+                                   : J[0][0] * K[0][0] + J[0][1] * K[1][0] + J[0][2] * K[2][0];
+  const double s = 1.0 / detJ;
+  double* g = Gc + (size_t)p * 6;
+  g[0] = (K[0][0] * K[0][0] + K[0][1] * K[0][1] + K[0][2] * K[0][2]) * s;
+  g[1] = (K[1][0] * K[0][0] + K[1][1] * K[0][1] + K[1][2] * K[0][2]) * s;
+  g[2] = (K[2][0] * K[0][0] + K[2][1] * K[0][1] + K[2][2] * K[0][2]) * s;
+  g[3] = (K[1][0] * K[1][0] + K[1][1] * K[1][1] + K[1][2] * K[1][2]) * s;
+  g[4] = (K[2][0] * K[1][0] + K[2][1] * K[1][1] + K[2][2] * K[1][2]) * s;
+  g[5] = (K[2][0] * K[2][0] + K[2][1] * K[2][1] + K[2][2] * K[2][2]) * s;
+}
+
 // diag(A) contributions, thread per (cell position, local dof); see DESIGN.md "diagonal".
 __global__ void k_diag(int P, const double* __restrict__ G, const int32_t* __restrict__ enc,
                        const int32_t* __restrict__ perm, const double* __restrict__ kappa,
@@ -1067,6 +1132,262 @@ void launch_apply_tma_t(pmgx_ctx* c, cudaStream_t st, const double* x, double* y
   }
 }
 
+// ------------------------------------------------ the affine-geometry apply kernel --
+// On a cell whose trilinear map is affine (every cell of a box / parallelepiped mesh, i.e. all
+// the benchmark meshes) J is constant, so G(q) = w_q * Gc with ONE 6-vector Gc = K K^T / det J per
+// cell: the 48 B per quadrature point that make up 79 % of the streamed bytes of the apply collapse
+// to 48 B per cell.  When ALL cells of an operator pass the affinity test at create
+// (k_cell_geometry, tolerance 1e-13 h) this kernel replaces k_apply_tma: same thread mapping and
+// arithmetic (thread = z-index of a cell, (ix,iy) slab in registers, z contraction through
+// shared memory), but nothing is streamed except the encoded dofmap (cp.async.bulk double
+// buffer); the kernel is then bound by the gather / atomic traffic of x and y in L2, not by HBM.
+// Meshes with any non-affine cell keep the streamed-G kernels; PMGX_LAP_STREAM_G forces them.
+template <int P, int TPB>
+struct AffCfg
+{
+  static constexpr int n = P + 1;
+  static constexpr int n2 = n * n;
+  static constexpr int tpb = TPB;
+  static constexpr int cpb = tpb / n;
+  static constexpr int SE = (cpb * n + 3) & ~3;
+  static constexpr int kp = n + (n & 1);
+  static constexpr int cs = ((n * kp / 2) & 1) ? n * kp : n * kp + 2;
+  static constexpr uint32_t enc_bytes = n2 * SE * sizeof(int32_t);
+  static constexpr int buf_doubles = 2 * cpb * cs;
+  static constexpr size_t off_su = 2 * (size_t)enc_bytes;
+  static constexpr size_t off_sf = off_su + (size_t)buf_doubles * sizeof(double);
+  static constexpr size_t off_bar = off_sf + (size_t)buf_doubles * sizeof(double);
+  static constexpr size_t smem = off_bar + 2 * sizeof(uint64_t);
+  static constexpr int minb = P <= 2 ? 6 : (TPB <= 64 ? 4 : 2);
+};
+
+template <int P, int TPB>
+__global__ void __launch_bounds__(TPB, AffCfg<P, TPB>::minb)
+k_apply_affine(const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ Gc,
+               const int32_t* __restrict__ enc, const int32_t* __restrict__ perm,
+               const double* __restrict__ kappa, long long batch0, int cell0, int count, int nbatch)
+{
+  using C = AffCfg<P, TPB>;
+  constexpr int n = C::n, n2 = C::n2, CPB = C::cpb, SE = C::SE, KP = C::kp, CS = C::cs;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int32_t* sE = reinterpret_cast<const int32_t*>(smraw);
+  double* su = reinterpret_cast<double*>(smraw + C::off_su);
+  double* sf = reinterpret_cast<double*>(smraw + C::off_sf);
+  uint64_t* fullE = reinterpret_cast<uint64_t*>(smraw + C::off_bar);
+
+  const int tid = threadIdx.x;
+  const int cl = tid / n;
+  const int k = tid - cl * n;
+  const bool in_block = cl < CPB;
+  const int cls = in_block ? cl : 0;
+  const int my_nb = ((int)blockIdx.x < nbatch) ? (nbatch - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  uint64_t pol = 0;
+  if (tid == 0)
+  {
+    mbar_init(&fullE[0], 1);
+    mbar_init(&fullE[1], 1);
+    mbar_fence_init();
+    pol = policy_evict_first();
+  }
+  __syncthreads();
+  auto issue_enc = [&](int it)
+  {
+    const long long gb = batch0 + blockIdx.x + (long long)it * gridDim.x;
+    mbar_expect_tx(&fullE[it & 1], C::enc_bytes);
+    bulk_g2s(const_cast<int32_t*>(sE) + (it & 1) * (n2 * SE), enc + gb * (long long)(n2 * SE), C::enc_bytes,
+             &fullE[it & 1], pol);
+  };
+  if (tid == 0 && my_nb > 0)
+    issue_enc(0);
+
+  double Dk[n], DTk[n];
+#pragma unroll
+  for (int l = 0; l < n; ++l)
+  {
+    Dk[l] = c_D[P][k * n + l];
+    DTk[l] = c_D[P][l * n + k];
+  }
+  const double wk = c_wts[P][k];
+
+  for (int it = 0; it < my_nb; ++it)
+  {
+    const int b = blockIdx.x + it * gridDim.x;
+    const int pl = b * CPB + cl;
+    const bool active = in_block && pl < count;
+
+    mbar_wait(&fullE[it & 1], (it >> 1) & 1);
+    const int32_t* dE = sE + (it & 1) * (n2 * SE) + tid;
+    double u[n2];
+    double g[6];
+    if (active)
+    {
+      const double kw = kappa[perm[cell0 + pl]] * wk; // kappa re-read on every apply (src/laplacian.hpp:230)
+      const double* gp = Gc + (size_t)(cell0 + pl) * 6;
+#pragma unroll
+      for (int c = 0; c < 6; ++c)
+        g[c] = gp[c] * kw;
+#pragma unroll
+      for (int a = 0; a < n2; ++a)
+      {
+        const int da = dE[a * SE];
+        const int idx = da < 0 ? ~da : da;
+        const double xv = x[idx];
+        if (da < 0)
+          y[idx] = xv; // Dirichlet row: y = x (src/laplacian.hpp:273-274)
+        u[a] = da < 0 ? 0.0 : xv;
+      }
+    }
+    else
+    {
+#pragma unroll
+      for (int c = 0; c < 6; ++c)
+        g[c] = 0.0;
+#pragma unroll
+      for (int a = 0; a < n2; ++a)
+        u[a] = 0.0;
+    }
+    if (in_block)
+    {
+#pragma unroll
+      for (int j = 0; j < n; ++j)
+        su[cl * CS + j * KP + k] = u[j];
+    }
+    __syncthreads(); // z-rows of plane 0 are visible; the other dofmap buffer (batch it-1) is free
+    if (tid == 0 && it + 1 < my_nb)
+      issue_enc(it + 1);
+
+    double acc[n2];
+#pragma unroll
+    for (int a = 0; a < n2; ++a)
+      acc[a] = 0.0;
+
+#pragma unroll
+    for (int i = 0; i < n; ++i)
+    {
+      const double* sup = su + ((i & 1) * CPB + cls) * CS;
+      double* sfz = sf + ((i & 1) * CPB + cls) * CS;
+      double fz[n];
+#pragma unroll
+      for (int j = 0; j < n; ++j)
+      {
+        double gx = 0.0, gy = 0.0, gz = 0.0;
+        const double2* row = reinterpret_cast<const double2*>(sup + j * KP);
+#pragma unroll
+        for (int l2 = 0; l2 < KP / 2; ++l2)
+        {
+          const double2 r = row[l2];
+          gz = fma(Dk[2 * l2], r.x, gz);
+          if (2 * l2 + 1 < n)
+            gz = fma(Dk[2 * l2 + 1], r.y, gz);
+        }
+#pragma unroll
+        for (int l = 0; l < n; ++l)
+        {
+          gx = fma(c_D[P][i * n + l], u[l * n + j], gx);
+          gy = fma(c_D[P][j * n + l], u[i * n + l], gy);
+        }
+        const double wij = c_wts[P][i] * c_wts[P][j]; // G(q) = w_i w_j w_k Gc
+        const double fx = wij * (g[0] * gx + g[1] * gy + g[2] * gz);
+        const double fy = wij * (g[1] * gx + g[3] * gy + g[4] * gz);
+        fz[j] = wij * (g[2] * gx + g[4] * gy + g[5] * gz);
+#pragma unroll
+        for (int l = 0; l < n; ++l)
+        {
+          acc[l * n + j] = fma(c_D[P][i * n + l], fx, acc[l * n + j]);
+          acc[i * n + l] = fma(c_D[P][j * n + l], fy, acc[i * n + l]);
+        }
+      }
+      if (in_block)
+      {
+#pragma unroll
+        for (int j = 0; j < n; ++j)
+          sfz[j * KP + k] = fz[j];
+        if (i + 1 < n)
+        {
+          double* sun = su + (((i + 1) & 1) * CPB + cl) * CS;
+#pragma unroll
+          for (int j = 0; j < n; ++j)
+            sun[j * KP + k] = u[(i + 1) * n + j];
+        }
+      }
+      __syncthreads(); // fz rows and the next z-rows are visible
+#pragma unroll
+      for (int j = 0; j < n; ++j)
+      {
+        const double2* row = reinterpret_cast<const double2*>(sfz + j * KP);
+        double t = 0.0;
+#pragma unroll
+        for (int q2 = 0; q2 < KP / 2; ++q2)
+        {
+          const double2 r = row[q2];
+          t = fma(DTk[2 * q2], r.x, t);
+          if (2 * q2 + 1 < n)
+            t = fma(DTk[2 * q2 + 1], r.y, t);
+        }
+        acc[i * n + j] += t;
+      }
+    }
+    if (active)
+    {
+#pragma unroll
+      for (int a = 0; a < n2; ++a)
+      {
+        const int da = dE[a * SE];
+        if (da >= 0)
+          atomicAdd(&y[da], acc[a]);
+      }
+    }
+  }
+}
+
+template <int P, int TPB>
+void launch_apply_affine_t(pmgx_ctx* c, cudaStream_t st, const double* x, double* y, const double* Gc,
+                           const int32_t* enc, const int32_t* perm, const double* kappa, long long batch0, int cell0,
+                           int count)
+{
+  using C = AffCfg<P, TPB>;
+  const bool timed = c->profiling && st == c->stream;
+  static int ctas_per_sm[64] = {0};
+  if (ctas_per_sm[c->device] == 0)
+  {
+    PMGX_CUDA(cudaFuncSetAttribute(k_apply_affine<P, TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem));
+    int nb = 0;
+    PMGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_apply_affine<P, TPB>, TPB, C::smem));
+    PMGX_REQUIRE(nb >= 1, "k_apply_affine<%d,%d> does not fit on an SM", P, TPB);
+    ctas_per_sm[c->device] = nb;
+  }
+  const int nbatch = (count + C::cpb - 1) / C::cpb;
+  const int grid = std::min(nbatch, ctas_per_sm[c->device] * c->num_sms);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (timed)
+  {
+    PMGX_CUDA(cudaEventCreate(&e0));
+    PMGX_CUDA(cudaEventCreate(&e1));
+    PMGX_CUDA(cudaEventRecord(e0, st));
+  }
+  k_apply_affine<P, TPB><<<grid, TPB, C::smem, st>>>(x, y, Gc, enc, perm, kappa, batch0, cell0, count, nbatch);
+  check_launch("k_apply_affine");
+  count_launch(c);
+  if (timed)
+  {
+    PMGX_CUDA(cudaEventRecord(e1, st));
+    c->prof[P].emplace_back(e0, e1);
+  }
+}
+
+template <int P>
+void launch_apply_affine(pmgx_ctx* c, cudaStream_t st, int tpb, const double* x, double* y, const double* Gc,
+                         const int32_t* enc, const int32_t* perm, const double* kappa, long long batch0, int cell0,
+                         int count)
+{
+  if (count <= 0)
+    return;
+  if (tpb == 64)
+    return launch_apply_affine_t<P, 64>(c, st, x, y, Gc, enc, perm, kappa, batch0, cell0, count);
+  return launch_apply_affine_t<P, 128>(c, st, x, y, Gc, enc, perm, kappa, batch0, cell0, count);
+}
+
 // default tuning (threads per CTA, geometry planes in flight); PMGX_TMA_TPB / PMGX_TMA_R override
 // (measured on B200, scripts/sweep_tma.sh: more, smaller CTAs with a 2-plane ring win for P3/P4)
 inline int tma_default_tpb(int P) { return (P == 1 || P >= 5) ? 64 : 128; }
@@ -1138,6 +1459,8 @@ struct Laplacian : pmgx_operator
   Lay lay;
   int tma_tpb = 128, tma_r = 2;
   bool use_tma = true; // TMA-pipelined slab kernel (default); PMGX_APPLY_KERNEL=slab|column for A/B runs
+  DevBuf<double> Gc;   // [n_list][6] per-cell geometry factor of affine cells
+  bool affine = false; // every cell affine: k_apply_affine replaces the streamed-G kernels
 
   int n_list() const { return n_l + n_b; }
 
@@ -1165,7 +1488,14 @@ struct Laplacian : pmgx_operator
     bool done = false;
     if constexpr (PP <= SLAB_MAX_DEGREE)
     {
-      if (lay.mode == 1 && use_tma)
+      if (lay.mode == 1 && affine)
+      {
+        launch_apply_affine<PP>(ctx, cs, tma_tpb, x, y, Gc.p, enc.p, perm.p, kappa, 0, 0, n_l);
+        join_before_boundary();
+        launch_apply_affine<PP>(ctx, bs, tma_tpb, x, y, Gc.p, enc.p, perm.p, kappa, lay.nb_l, n_l, n_b);
+        done = true;
+      }
+      else if (lay.mode == 1 && use_tma)
       {
         launch_apply_tma<PP>(ctx, cs, tma_tpb, tma_r, x, y, G.p, enc.p, perm.p, kappa, 0, 0, n_l); // :406-409
         join_before_boundary();
@@ -1307,6 +1637,24 @@ int pmgx_laplacian_create(pmgx_ctx* ctx, int degree, int n_cells, const int32_t*
         (flags & PMGX_LAP_LITERAL_DETJ) != 0, lay);
     pmgx::check_launch("k_geometry");
     pmgx::count_launch(ctx, 2);
+    // affine cells: one geometry 6-vector per cell instead of one per quadrature point
+    if (lay.mode == 1 && !force && !(flags & PMGX_LAP_STREAM_G))
+    {
+      L->Gc.alloc((size_t)n_list * 6);
+      pmgx::DevBuf<int> bad;
+      bad.alloc(1);
+      PMGX_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), ctx->stream));
+      pmgx::k_cell_geometry<<<(n_list + 255) / 256, 256, 0, ctx->stream>>>(
+          xgeom, geom_dofmap, L->perm.p, L->Gc.p, n_list, (flags & PMGX_LAP_LITERAL_DETJ) != 0, 1e-13, bad.p);
+      pmgx::check_launch("k_cell_geometry");
+      pmgx::count_launch(ctx);
+      int n_bad = 0;
+      PMGX_CUDA(cudaMemcpyAsync(&n_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      PMGX_CUDA(cudaStreamSynchronize(ctx->stream));
+      L->affine = n_bad == 0;
+      if (!L->affine)
+        L->Gc.release();
+    }
   }
   L->diag_inv.alloc((size_t)n_owned);
   if (!(flags & PMGX_LAP_NO_DIAG) && n_owned > 0)
@@ -1348,6 +1696,11 @@ int pmgx_laplacian_get_G(pmgx_operator* op, double* G_out)
     pmgx::count_launch(L->ctx);
   }
   PMGX_API_END
+}
+
+int pmgx_laplacian_is_affine(pmgx_operator* op)
+{
+  return op && op->kind == pmgx_operator::LAPLACIAN && static_cast<Laplacian*>(op)->affine ? 1 : 0;
 }
 
 int pmgx_laplacian_rhs(pmgx_operator* op, const double* fvals, double g, double* b)
