@@ -293,6 +293,10 @@ class MatFreeLaplacian(_Operator):
         self.h = h
         self.n_list = len(lc) + len(bc_)
 
+    def is_affine(self):
+        """True when the apply runs the affine-geometry kernel (one geometry 6-vector per cell)."""
+        return bool(lib.pmgx_laplacian_is_affine(self.h))
+
     def geometry_factors(self):
         nq = (self.degree + 1) ** 3
         G = self.ctx.zeros(self.n_list * nq * 6)
