@@ -125,3 +125,34 @@ def test_unsupported_degree_and_size_errors(ctx):
     a, b = api.Vector(ctx, 5), api.Vector(ctx, 6)
     with pytest.raises(api.PmgxError, match="Incompatible vector sizes"):
         api.inner_product(a, b)
+
+
+@pytest.mark.parametrize("P", [1, 2, 3, 4, 5, 6])
+def test_affine_geometry_kernel_on_a_sheared_box(ctx, P):
+    """Every cell of a linearly mapped box is a parallelepiped: the operator takes the affine-geometry
+    kernel (one geometry 6-vector per cell, G(q) = w_q Gc with all six components non-zero) and must
+    give the oracle's action, the streamed-G kernel's action (PMGX_LAP_STREAM_G) and the same
+    diagonal; a single displaced vertex sends the operator back to the streamed kernels."""
+    mesh = om.create_box(4, 3, 5)
+    M = np.array([[1.0, 0.3, -0.2], [0.1, 0.9, 0.25], [-0.15, 0.2, 1.1]])
+    mesh.verts[:] = mesh.verts @ M.T + np.array([0.3, -1.0, 2.0])
+    ol = OracleLevel(mesh, P)
+    assert np.abs(ol.G[:, :, [1, 2, 4]]).max() > 1e-3          # genuinely non-diagonal geometry
+    gl, gs = GpuLevel(ctx, ol), GpuLevel(ctx, ol, flags=4)
+    assert gl.op.is_affine() and not gs.op.is_affine()
+    x = np.random.default_rng(P).uniform(-1, 1, ol.nd)
+    ya, ys, yo = gl.apply(x), gs.apply(x), ol.A(x)
+    assert rel(ya, yo)[1] < 1e-12 and rel(ys, yo)[1] < 1e-12 and rel(ya, ys)[1] < 1e-13
+    # ragged batches / split lists through the affine kernel
+    nc = mesh.ncells
+    cells = np.arange(nc, dtype=np.int32)
+    g2 = GpuLevel(ctx, ol, lcells=cells[: nc // 3], bcells=cells[nc // 3:])
+    assert g2.op.is_affine() and rel(g2.apply(x), yo)[1] < 1e-12
+    # one displaced vertex: not affine any more, still correct
+    mesh2 = om.create_box(4, 3, 5)
+    mesh2.verts[:] = mesh2.verts @ M.T
+    mesh2.verts[37] += 1e-6
+    ol2 = OracleLevel(mesh2, P)
+    gl2 = GpuLevel(ctx, ol2)
+    assert not gl2.op.is_affine()
+    assert rel(gl2.apply(x), ol2.A(x))[1] < 1e-12
