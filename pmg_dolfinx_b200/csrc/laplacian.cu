@@ -560,7 +560,7 @@ template <int P>
 void launch_apply(pmgx_ctx* c, cudaStream_t st, const double* x, double* y, const double* G, const int32_t* enc,
                   const int32_t* perm, const double* kappa, int first, int count)
 {
-  const bool timed = c->profiling && st == c->stream; // launches on the halo stream overlap the interior kernel
+  const bool timed = c->profiling && first == 0; // per-kernel timing covers the interior-cell launch only
   if (count <= 0)
     return;
   using C = ApplyCfg<P>;
@@ -771,7 +771,7 @@ template <int P>
 void launch_apply_slab(pmgx_ctx* c, cudaStream_t st, const double* x, double* y, const double* G, const int32_t* enc,
                        const int32_t* perm, const double* kappa, long long batch0, int cell0, int count)
 {
-  const bool timed = c->profiling && st == c->stream;
+  const bool timed = c->profiling && cell0 == 0; // per-kernel timing covers the interior-cell launch only
   if (count <= 0)
     return;
   using C = SlabCfg<P>;
@@ -1100,7 +1100,7 @@ template <int P, int TPB, int R>
 void launch_apply_tma_t(pmgx_ctx* c, cudaStream_t st, const double* x, double* y, const double* G, const int32_t* enc,
                         const int32_t* perm, const double* kappa, long long batch0, int cell0, int count)
 {
-  const bool timed = c->profiling && st == c->stream;
+  const bool timed = c->profiling && cell0 == 0; // per-kernel timing covers the interior-cell launch only
   using C = TmaCfg<P, TPB, R>;
   static int ctas_per_sm[64] = {0};
   if (ctas_per_sm[c->device] == 0)
@@ -1341,13 +1341,215 @@ k_apply_affine(const double* __restrict__ x, double* __restrict__ y, const doubl
   }
 }
 
+// Shuffle variant of the affine kernel: a warp holds 32/n whole cells (lanes beyond that idle), so
+// the z contractions are warp shuffles from the n lanes of the thread's own cell -- no shared-memory
+// rows, no block barrier per plane.  ncu on the shared-memory variant at P4: L1/shared data pipe 78 %
+// busy with 20 %-efficient broadcast reads; n double shuffles move the same data in ~40 % fewer
+// pipe cycles and the warps of a CTA no longer wait for each other.
+template <int P, int TPB>
+struct AffShCfg
+{
+  static constexpr int n = P + 1;
+  static constexpr int n2 = n * n;
+  static constexpr int tpb = TPB;
+  static constexpr int cpw = 32 / n;               // cells per warp
+  static constexpr int cpb = (TPB / 32) * cpw;     // cells per batch
+  static constexpr int SE = (cpb * n + 3) & ~3;
+  static constexpr uint32_t enc_bytes = n2 * SE * sizeof(int32_t);
+  static constexpr size_t off_bar = 2 * (size_t)enc_bytes;
+  static constexpr size_t smem = off_bar + 2 * sizeof(uint64_t);
+  static constexpr int minb = P <= 2 ? 6 : (TPB <= 64 ? 4 : 2);
+};
+
+template <int P, int TPB>
+__global__ void __launch_bounds__(TPB, AffShCfg<P, TPB>::minb)
+k_apply_affine_shfl(const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ Gc,
+                    const int32_t* __restrict__ enc, const int32_t* __restrict__ perm,
+                    const double* __restrict__ kappa, long long batch0, int cell0, int count, int nbatch)
+{
+  using C = AffShCfg<P, TPB>;
+  constexpr int n = C::n, n2 = C::n2, CPB = C::cpb, CPW = C::cpw, SE = C::SE;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int32_t* sE = reinterpret_cast<const int32_t*>(smraw);
+  uint64_t* fullE = reinterpret_cast<uint64_t*>(smraw + C::off_bar);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int cw = lane / n;                 // cell within the warp
+  const int k = lane - cw * n;             // iz
+  const bool lane_ok = cw < CPW;
+  const int cl = warp * CPW + (lane_ok ? cw : 0);
+  const int base = (lane_ok ? cw : 0) * n; // first lane of this thread's cell
+  const int slot = cl * n + (lane_ok ? k : 0);
+  const int my_nb = ((int)blockIdx.x < nbatch) ? (nbatch - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  uint64_t pol = 0;
+  if (tid == 0)
+  {
+    mbar_init(&fullE[0], 1);
+    mbar_init(&fullE[1], 1);
+    mbar_fence_init();
+    pol = policy_evict_first();
+  }
+  __syncthreads();
+  auto issue_enc = [&](int it)
+  {
+    const long long gb = batch0 + blockIdx.x + (long long)it * gridDim.x;
+    mbar_expect_tx(&fullE[it & 1], C::enc_bytes);
+    bulk_g2s(const_cast<int32_t*>(sE) + (it & 1) * (n2 * SE), enc + gb * (long long)(n2 * SE), C::enc_bytes,
+             &fullE[it & 1], pol);
+  };
+  if (tid == 0 && my_nb > 0)
+  {
+    issue_enc(0);
+    if (my_nb > 1)
+      issue_enc(1);
+  }
+
+  const int kk = lane_ok ? k : 0;
+  double Dk[n], DTk[n];
+#pragma unroll
+  for (int l = 0; l < n; ++l)
+  {
+    Dk[l] = c_D[P][kk * n + l];
+    DTk[l] = c_D[P][l * n + kk];
+  }
+  const double wk = c_wts[P][kk];
+
+  for (int it = 0; it < my_nb; ++it)
+  {
+    const int b = blockIdx.x + it * gridDim.x;
+    const int pl = b * CPB + cl;
+    const bool active = lane_ok && pl < count;
+
+    mbar_wait(&fullE[it & 1], (it >> 1) & 1);
+    const int32_t* dE = sE + (it & 1) * (n2 * SE) + slot;
+    double u[n2];
+    double g[6];
+    if (active)
+    {
+      const double kw = kappa[perm[cell0 + pl]] * wk; // kappa re-read on every apply (src/laplacian.hpp:230)
+      const double* gp = Gc + (size_t)(cell0 + pl) * 6;
+#pragma unroll
+      for (int c = 0; c < 6; ++c)
+        g[c] = gp[c] * kw;
+#pragma unroll
+      for (int a = 0; a < n2; ++a)
+      {
+        const int da = dE[a * SE];
+        const int idx = da < 0 ? ~da : da;
+        const double xv = x[idx];
+        if (da < 0)
+          y[idx] = xv; // Dirichlet row: y = x (src/laplacian.hpp:273-274)
+        u[a] = da < 0 ? 0.0 : xv;
+      }
+    }
+    else
+    {
+#pragma unroll
+      for (int c = 0; c < 6; ++c)
+        g[c] = 0.0;
+#pragma unroll
+      for (int a = 0; a < n2; ++a)
+        u[a] = 0.0;
+    }
+    double acc[n2];
+#pragma unroll
+    for (int a = 0; a < n2; ++a)
+      acc[a] = 0.0;
+
+#pragma unroll
+    for (int i = 0; i < n; ++i)
+    {
+#pragma unroll
+      for (int j = 0; j < n; ++j)
+      {
+        double gx = 0.0, gy = 0.0, gz = 0.0;
+        const double uij = u[i * n + j];
+#pragma unroll
+        for (int l = 0; l < n; ++l)
+        {
+          gz = fma(Dk[l], __shfl_sync(0xffffffffu, uij, base + l), gz);
+          gx = fma(c_D[P][i * n + l], u[l * n + j], gx);
+          gy = fma(c_D[P][j * n + l], u[i * n + l], gy);
+        }
+        const double wij = c_wts[P][i] * c_wts[P][j]; // G(q) = w_i w_j w_k Gc
+        const double fx = wij * (g[0] * gx + g[1] * gy + g[2] * gz);
+        const double fy = wij * (g[1] * gx + g[3] * gy + g[4] * gz);
+        const double fz = wij * (g[2] * gx + g[4] * gy + g[5] * gz);
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < n; ++q)
+          t = fma(DTk[q], __shfl_sync(0xffffffffu, fz, base + q), t);
+#pragma unroll
+        for (int l = 0; l < n; ++l)
+        {
+          acc[l * n + j] = fma(c_D[P][i * n + l], fx, acc[l * n + j]);
+          acc[i * n + l] = fma(c_D[P][j * n + l], fy, acc[i * n + l]);
+        }
+        acc[i * n + j] += t;
+      }
+    }
+    if (active)
+    {
+#pragma unroll
+      for (int a = 0; a < n2; ++a)
+      {
+        const int da = dE[a * SE];
+        if (da >= 0)
+          atomicAdd(&y[da], acc[a]);
+      }
+    }
+    // every thread is done with this batch's dofmap buffer before the one after next may land in it
+    __syncthreads();
+    if (tid == 0 && it + 2 < my_nb)
+      issue_enc(it + 2);
+  }
+}
+
+template <int P, int TPB>
+void launch_apply_affine_shfl_t(pmgx_ctx* c, cudaStream_t st, const double* x, double* y, const double* Gc,
+                                const int32_t* enc, const int32_t* perm, const double* kappa, long long batch0,
+                                int cell0, int count)
+{
+  using C = AffShCfg<P, TPB>;
+  const bool timed = c->profiling && cell0 == 0; // per-kernel timing covers the interior-cell launch only
+  static int ctas_per_sm[64] = {0};
+  if (ctas_per_sm[c->device] == 0)
+  {
+    PMGX_CUDA(cudaFuncSetAttribute(k_apply_affine_shfl<P, TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)C::smem));
+    int nb = 0;
+    PMGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_apply_affine_shfl<P, TPB>, TPB, C::smem));
+    PMGX_REQUIRE(nb >= 1, "k_apply_affine_shfl<%d,%d> does not fit on an SM", P, TPB);
+    ctas_per_sm[c->device] = nb;
+  }
+  const int nbatch = (count + C::cpb - 1) / C::cpb;
+  const int grid = std::min(nbatch, ctas_per_sm[c->device] * c->num_sms);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (timed)
+  {
+    PMGX_CUDA(cudaEventCreate(&e0));
+    PMGX_CUDA(cudaEventCreate(&e1));
+    PMGX_CUDA(cudaEventRecord(e0, st));
+  }
+  k_apply_affine_shfl<P, TPB><<<grid, TPB, C::smem, st>>>(x, y, Gc, enc, perm, kappa, batch0, cell0, count, nbatch);
+  check_launch("k_apply_affine_shfl");
+  count_launch(c);
+  if (timed)
+  {
+    PMGX_CUDA(cudaEventRecord(e1, st));
+    c->prof[P].emplace_back(e0, e1);
+  }
+}
+
 template <int P, int TPB>
 void launch_apply_affine_t(pmgx_ctx* c, cudaStream_t st, const double* x, double* y, const double* Gc,
                            const int32_t* enc, const int32_t* perm, const double* kappa, long long batch0, int cell0,
                            int count)
 {
   using C = AffCfg<P, TPB>;
-  const bool timed = c->profiling && st == c->stream;
+  const bool timed = c->profiling && cell0 == 0; // per-kernel timing covers the interior-cell launch only
   static int ctas_per_sm[64] = {0};
   if (ctas_per_sm[c->device] == 0)
   {
@@ -1377,12 +1579,16 @@ void launch_apply_affine_t(pmgx_ctx* c, cudaStream_t st, const double* x, double
 }
 
 template <int P>
-void launch_apply_affine(pmgx_ctx* c, cudaStream_t st, int tpb, const double* x, double* y, const double* Gc,
-                         const int32_t* enc, const int32_t* perm, const double* kappa, long long batch0, int cell0,
-                         int count)
+void launch_apply_affine(pmgx_ctx* c, cudaStream_t st, bool shfl, int tpb, const double* x, double* y,
+                         const double* Gc, const int32_t* enc, const int32_t* perm, const double* kappa,
+                         long long batch0, int cell0, int count)
 {
   if (count <= 0)
     return;
+  if (shfl && tpb == 64)
+    return launch_apply_affine_shfl_t<P, 64>(c, st, x, y, Gc, enc, perm, kappa, batch0, cell0, count);
+  if (shfl)
+    return launch_apply_affine_shfl_t<P, 128>(c, st, x, y, Gc, enc, perm, kappa, batch0, cell0, count);
   if (tpb == 64)
     return launch_apply_affine_t<P, 64>(c, st, x, y, Gc, enc, perm, kappa, batch0, cell0, count);
   return launch_apply_affine_t<P, 128>(c, st, x, y, Gc, enc, perm, kappa, batch0, cell0, count);
@@ -1464,6 +1670,7 @@ struct Laplacian : pmgx_operator
   bool use_tma = true; // TMA-pipelined slab kernel (default); PMGX_APPLY_KERNEL=slab|column for A/B runs
   DevBuf<double> Gc;   // [n_list][6] per-cell geometry factor of affine cells
   bool affine = false; // every cell affine: k_apply_affine replaces the streamed-G kernels
+  bool aff_shfl = false; // z contractions by warp shuffles instead of shared-memory rows (default for P <= 2)
 
   int n_list() const { return n_l + n_b; }
 
@@ -1493,9 +1700,9 @@ struct Laplacian : pmgx_operator
     {
       if (lay.mode == 1 && affine)
       {
-        launch_apply_affine<PP>(ctx, cs, tma_tpb, x, y, Gc.p, enc.p, perm.p, kappa, 0, 0, n_l);
+        launch_apply_affine<PP>(ctx, cs, aff_shfl, tma_tpb, x, y, Gc.p, enc.p, perm.p, kappa, 0, 0, n_l);
         join_before_boundary();
-        launch_apply_affine<PP>(ctx, bs, tma_tpb, x, y, Gc.p, enc.p, perm.p, kappa, lay.nb_l, n_l, n_b);
+        launch_apply_affine<PP>(ctx, bs, aff_shfl, tma_tpb, x, y, Gc.p, enc.p, perm.p, kappa, lay.nb_l, n_l, n_b);
         done = true;
       }
       else if (lay.mode == 1 && use_tma)
@@ -1635,7 +1842,13 @@ int pmgx_laplacian_create(pmgx_ctx* ctx, int degree, int n_cells, const int32_t*
   if (!L->use_tma)
     L->tma_tpb = 128;
   PMGX_REQUIRE(L->tma_tpb == 64 || L->tma_tpb == 128, "PMGX_TMA_TPB must be 64 or 128");
-  lay.cpb = L->tma_tpb / n;
+  // measured at 100 M dofs (shuffle vs shared-memory z contraction): P1 3.52 vs 3.45 ms, P2 1.58 vs 1.67,
+  // P3 1.63 vs 1.54, P4 1.36 vs 1.28, P5 1.57 vs 1.19, P6 2.27 vs 2.03 -- double shuffles cost two issue
+  // slots each and only pay where the element is small
+  L->aff_shfl = degree == 2;
+  if (const char* e = getenv("PMGX_AFFINE_SHFL"))
+    L->aff_shfl = atoi(e) != 0;
+  lay.cpb = (L->affine && L->aff_shfl) ? (L->tma_tpb / 32) * (32 / n) : L->tma_tpb / n;
   lay.S = (lay.cpb * n + 1) & ~1;
   lay.SE = (lay.cpb * n + 3) & ~3;
   lay.nb_l = (n_lcells + lay.cpb - 1) / lay.cpb;
