@@ -169,7 +169,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "Gdof/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "examples/pmg P4->P2->P1 V-cycle (BASELINE configs[4]), CPU sample",
+            "config": {"workload": "examples/pmg: P4->P2->P1 V-cycle, ~100M P4 dofs per GPU (BASELINE configs[4])",
+                       "sample": cb["sample"],
                        "degrees": list(DEGREES), "smoother_its": NSMOOTH, "coarse": f"CSR Jacobi-PCG <= {COARSE_ITS} its",
                        "note": "reference's DOLFINx/PETSc CPU path not installable here; oracle C/OpenMP port timed"},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
