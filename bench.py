@@ -140,6 +140,13 @@ def cpu_vcycle_setup(n_cells_1d):
 
 
 def cpu_baseline(steps=2, warmup=1, n=24):
+    # the hot kernels are the oracle's C/OpenMP routines; numpy's BLAS pool must not spin next to
+    # libgomp's threads (measured: 306 -> 61 ms per V-cycle on 8 cores with the BLAS pool at 1 thread)
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=1, user_api="blas")
+    except Exception:
+        pass
     step, nd, threads, A = cpu_vcycle_setup(n)
     u = np.zeros(nd)
     for _ in range(warmup):
