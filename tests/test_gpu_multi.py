@@ -10,14 +10,17 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("p2p", ["1", "0"], ids=["nvlink-p2p", "nccl"])
+@pytest.mark.parametrize("p2p,perturb", [("1", "0.15"), ("0", "0.15"), ("1", "0.0")],
+                         ids=["nvlink-p2p", "nccl", "nvlink-p2p-affine-mesh"])
 @pytest.mark.parametrize("nranks", [2, 4, 8])
-def test_multi_gpu_matches_oracle(nranks, p2p):
+def test_multi_gpu_matches_oracle(nranks, p2p, perturb):
     import torch
     if not torch.cuda.is_available() or torch.cuda.device_count() < nranks:
         pytest.skip(f"needs {nranks} GPUs")
-    port = 29600 + nranks + 20 * int(p2p)
-    env = dict(os.environ, PMGX_P2P=p2p)   # "0": NCCL send/recv + ncclAllReduce instead of the peer-memory kernels
+    port = 29600 + nranks + 20 * int(p2p) + (40 if perturb == "0.0" else 0)
+    # "0": NCCL send/recv + ncclAllReduce instead of the peer-memory kernels; perturb 0: every cell is
+    # affine, so the interior / boundary launches go through the affine-geometry kernel
+    env = dict(os.environ, PMGX_P2P=p2p, PMGX_CHECK_PERTURB=perturb)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nranks}",
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "scripts", "mgpu_check.py")]
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600, env=env)
