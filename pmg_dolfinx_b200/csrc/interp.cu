@@ -126,9 +126,27 @@ k_prolong(const __grid_constant__ InterpTab tab, const int32_t* __restrict__ cel
 #pragma unroll
   for (int cz = 0; cz < NC; ++cz)
     mk[cz] = tab.m[k * NC + cz];
+  // all global loads of the thread are issued before any arithmetic (the kernel is latency-bound:
+  // ncu long_scoreboard 25 stalls per issue with the loads interleaved): NC^3 coarse values ...
+  const int32_t* sc = s_c + c * NC3;
+  const int32_t* sf = s_f + c * NF3 + k;
+  double cv[NC3];
+#pragma unroll
+  for (int t = 0; t < NC3; ++t)
+    cv[t] = xc[sc[t]];
+  // ... and, when adding, the NF^2 fine values this thread owns
+  double xo[ADD ? NF * NF : 1];
+  if (ADD)
+  {
+#pragma unroll
+    for (int t = 0; t < NF * NF; ++t)
+    {
+      const int32_t d = sf[t * NF];
+      xo[t] = (d >= 0 && d < n_owned_f) ? xf[d] : 0.0;
+    }
+  }
   // z pass: v[ix][iy] = sum_cz M[k][cz] xc[ix][iy][cz]
   double v[NC][NC];
-  const int32_t* sc = s_c + c * NC3;
 #pragma unroll
   for (int ix = 0; ix < NC; ++ix)
 #pragma unroll
@@ -137,7 +155,7 @@ k_prolong(const __grid_constant__ InterpTab tab, const int32_t* __restrict__ cel
       double s = 0.0;
 #pragma unroll
       for (int cz = 0; cz < NC; ++cz)
-        s = fma(mk[cz], xc[sc[(ix * NC + iy) * NC + cz]], s);
+        s = fma(mk[cz], cv[(ix * NC + iy) * NC + cz], s);
       v[ix][iy] = s;
     }
   // y pass: w[ix][fy] = sum_iy M[fy][iy] v[ix][iy]
@@ -154,7 +172,6 @@ k_prolong(const __grid_constant__ InterpTab tab, const int32_t* __restrict__ cel
       w[ix][fy] = s;
     }
   // x pass + store by the unique writer
-  const int32_t* sf = s_f + c * NF3 + k;
 #pragma unroll
   for (int fx = 0; fx < NF; ++fx)
 #pragma unroll
@@ -170,7 +187,7 @@ k_prolong(const __grid_constant__ InterpTab tab, const int32_t* __restrict__ cel
         if (ADD)
         {
           if (d < n_owned_f)
-            xf[d] = s * 1.0 + xf[d];
+            xf[d] = s * 1.0 + xo[fx * NF + fy];
         }
         else
           xf[d] = s;
@@ -220,20 +237,37 @@ k_restrict(const __grid_constant__ InterpTab tab, const int32_t* __restrict__ ce
     const int32_t* sf = s_f + c * NF3 + k;
     if (active)
     {
-#pragma unroll
-      for (int fx = 0; fx < NF; ++fx)
+      // gathers run one fx-slice ahead of the arithmetic (latency-bound kernel: 3 NF loads in flight)
+      double fv[2][NF], sv2[2][NF], mv[2][NF];
+      auto load_slice = [&](int fx, int b)
+      {
 #pragma unroll
         for (int fy = 0; fy < NF; ++fy)
         {
           const int32_t d = sf[(fx * NF + fy) * NF];
-          double val = xf[d];
-          if (sub != nullptr && d < n_owned_f)
-            val = sub[d] * (-1.0) + val;
-          val *= inv_mult[d]; // src/interpolate.hpp:82
+          fv[b][fy] = xf[d];
+          sv2[b][fy] = (sub != nullptr && d < n_owned_f) ? sub[d] : 0.0;
+          mv[b][fy] = inv_mult[d];
+        }
+      };
+      load_slice(0, 0);
+#pragma unroll
+      for (int fx = 0; fx < NF; ++fx)
+      {
+        if (fx + 1 < NF)
+          load_slice(fx + 1, (fx + 1) & 1);
+#pragma unroll
+        for (int fy = 0; fy < NF; ++fy)
+        {
+          double val = fv[fx & 1][fy];
+          if (sub != nullptr)
+            val = sv2[fx & 1][fy] * (-1.0) + val; // ghost entries carry 0 here: x - 0 is exact
+          val *= mv[fx & 1][fy]; // src/interpolate.hpp:82
 #pragma unroll
           for (int ix = 0; ix < NC; ++ix)
             w[ix][fy] = fma(tab.m[fx * NC + ix], val, w[ix][fy]);
         }
+      }
     }
     // transposed y pass: v[ix][iy] = sum_fy M[fy][iy] w[ix][fy]; handed to the z pass through smem
     double* sv = s_v + (c * NF + k) * NC2;

@@ -8,12 +8,15 @@
 //
 // Design (not a port): cells are re-laid-out at create time in launch order (lcells then
 // bcells); the dofmap is snapshotted with the Dirichlet marker folded into the sign bit, so
-// the apply never gathers bc_marker; G is stored component-major per cell, G[p][6][nq], so
-// every warp load of a G component is one contiguous run.  The apply kernel maps a thread to
-// one (iy,iz) column of a cell and keeps the x-direction in registers: the x contractions
-// never touch shared memory, the y/z contractions read planes from shared memory, and the
-// element is streamed plane by plane so only 2 small plane buffers are exchanged between
-// threads.  G is streamed with evict-first loads and software-prefetched one plane ahead.
+// the apply never gathers bc_marker; G is stored component-major per batch of cells so that one
+// (ix) plane of a batch is one contiguous cp.async.bulk transaction.  Apply kernels:
+//   k_apply_affine / k_apply_affine_shfl   every cell affine: one geometry 6-vector per cell
+//   k_apply_tma                            streamed G through a TMA ring (P1..P6)
+//   k_apply_slab                           same thread mapping, register-streamed G (A/B runs)
+//   k_apply                                column kernel (P7, P8)
+// In the slab kernels a thread owns one z-index of a cell and keeps the (ix,iy) slab of the
+// element in registers: the x and y contractions are register FMAs against constant-memory
+// derivative entries, only the z contraction crosses threads.
 #include "common.hpp"
 #include "operator.hpp"
 #include "csr.hpp"
