@@ -13,9 +13,15 @@ Pinning status (see DESIGN.md section "Oracle"):
                           (laplacian.hpp, interpolate.hpp, csr.hpp, vector.hpp)
                           are compiled from /root/reference into oracle/_ref/
                           (see oracle/ref_build/) and compared on the GPU box.
-  * everything else    -- parity unpinned by the reference (it holds no other
-                          numeric fixtures and DOLFINx/Basix/PETSc are absent);
-                          pinned by analytic known answers in tests/.
+  * Chebyshev-4, CG,   -- the reference's own Python prototypes
+    Lanczos estimate     (python_tests/chebyshev.py, cg.py, tqli.py) are run in the
+                          build container on a small SPD matrix with only their
+                          dolfinx/petsc4py IMPORTS stubbed
+                          (scripts/make_golden_solvers.py); their outputs are the
+                          fixture tests/golden/solvers_ref.npz.
+  * V-cycle, partition -- parity unpinned by the reference (python_tests/pmg.py is a
+                          DOLFINx script, not importable; no numeric fixtures);
+                          pinned by the oracle and analytic known answers in tests/.
 
 Numerical conventions: GLL nodes == GLL quadrature
 points on [0, 1] in ascending order; hex local dof index = ix*nd^2 + iy*nd + iz
