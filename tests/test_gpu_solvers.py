@@ -203,7 +203,8 @@ def _build_hierarchy(ctx, mesh, degrees, nsmooth=2):
     return ols, gls, olev, smoothers, interps, pro, res
 
 
-@pytest.mark.parametrize("degrees,n,coarse", [((1, 3), (10, 10, 10), False), ((1, 3), (6, 6, 6), True),
+@pytest.mark.parametrize("degrees,n,coarse", [((1, 3), (10, 10, 10), False), ((1, 3), (12, 12, 12), False),
+                                                ((1, 3), (6, 6, 6), True),
                                                 ((1, 2, 4), (4, 4, 4), False), ((1, 2, 4), (4, 4, 4), True)])
 def test_vcycle_history(ctx, degrees, n, coarse):
     """Config 1 (python_tests/pmg.py: 10^3 cells, P3->P1) and a 3-level P4->P2->P1 cycle: per-stage
