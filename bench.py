@@ -442,7 +442,12 @@ def run_gpu(args):
         kname = f"k_apply_affine<{Ptop},64>" if affine else f"k_apply_tma<{Ptop},128,2>"
         traffic, traffic_src = measured_traffic(Ptop, len(mesh.lcells), f"{Ptop}_affine" if affine else str(Ptop))
         B_own = own_bytes(Ptop, len(mesh.lcells), n_owned * frac_int) if affine else B_launch
-        cb = cpu_baseline(n=args.cpu_cells) if world == 1 and not args.no_cpu else None
+        cb = None
+        if world == 1 and not args.no_cpu:
+            try:
+                cb = cpu_baseline(n=args.cpu_cells)
+            except Exception as e:  # the CPU leg must never take the GPU line down with it
+                sys.stderr.write(f"cpu_baseline failed: {e}\n")
         line = {
             "metric": METRIC, "value": nd_global / ms_per_step / 1e6, "unit": "Gdof/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
