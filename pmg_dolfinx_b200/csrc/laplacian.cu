@@ -1277,13 +1277,14 @@ k_apply_affine(const double* __restrict__ x, double* __restrict__ y, const doubl
         double gx = 0.0, gy = 0.0, gz = 0.0;
         const double2* row = reinterpret_cast<const double2*>(sup + j * KP);
 #pragma unroll
-        for (int l2 = 0; l2 < KP / 2; ++l2)
+        for (int l2 = 0; l2 < n / 2; ++l2)
         {
           const double2 r = row[l2];
           gz = fma(Dk[2 * l2], r.x, gz);
-          if (2 * l2 + 1 < n)
-            gz = fma(Dk[2 * l2 + 1], r.y, gz);
+          gz = fma(Dk[2 * l2 + 1], r.y, gz);
         }
+        if (n & 1) // odd n: the last entry alone (a 64-bit load: half the wavefronts of a padded 128-bit one)
+          gz = fma(Dk[n - 1], sup[j * KP + n - 1], gz);
 #pragma unroll
         for (int l = 0; l < n; ++l)
         {
@@ -1321,13 +1322,14 @@ k_apply_affine(const double* __restrict__ x, double* __restrict__ y, const doubl
         const double2* row = reinterpret_cast<const double2*>(sfz + j * KP);
         double t = 0.0;
 #pragma unroll
-        for (int q2 = 0; q2 < KP / 2; ++q2)
+        for (int q2 = 0; q2 < n / 2; ++q2)
         {
           const double2 r = row[q2];
           t = fma(DTk[2 * q2], r.x, t);
-          if (2 * q2 + 1 < n)
-            t = fma(DTk[2 * q2 + 1], r.y, t);
+          t = fma(DTk[2 * q2 + 1], r.y, t);
         }
+        if (n & 1)
+          t = fma(DTk[n - 1], sfz[j * KP + n - 1], t);
         acc[i * n + j] += t;
       }
     }
