@@ -291,7 +291,6 @@ def run_gpu(args):
         pmg.apply(b, u)
     e1.record(ctx.stream)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
     import ctypes
     kms, kl = ctypes.c_double(), ctypes.c_longlong()
@@ -428,6 +427,9 @@ def run_gpu(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms = float(te.item())
     torch.cuda.set_stream(ctx.stream)
+    # sampled from before the timed V-cycles until here: the timed region, the apply loops and the
+    # end-to-end loop are all GPU-loaded (100 ms sampling period: the timed region alone yields 1-2 samples)
+    clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
         peak, peak_src = measured_peak()
