@@ -49,6 +49,7 @@ typedef struct pmgx_interp pmgx_interp;
 typedef struct pmgx_coarse pmgx_coarse;
 typedef struct pmgx_vcycle pmgx_vcycle;
 typedef struct pmgx_boxmesh pmgx_boxmesh;
+typedef struct pmgx_amg_hier pmgx_amg_hier;
 
 /* ------------------------------------------------------------------ misc -- */
 const char* pmgx_last_error_string(void);
@@ -242,6 +243,22 @@ int pmgx_coarse_solve(pmgx_coarse* cs, double* x, const double* b, int* iters_h)
  * the residual every 8 iterations, so the count is a multiple of 8 or max_iter */
 int pmgx_coarse_last_iterations(pmgx_coarse* cs);
 int pmgx_coarse_destroy(pmgx_coarse* cs);
+
+/* ------------------------------------- multilevel coarse solver: host set-up -- */
+/* First half of the smoothed-aggregation coarse solver that is to stand where the reference runs
+ * PETSc CG + BoomerAMG (src/amg.hpp:33-47).  Pure host code, no GPU needed, single-rank matrices
+ * (every column owned).  NOT yet used by pmgx_coarse_solve / the V-cycle: it builds the hierarchy
+ * (A_l, P_l, lambda_max(D^-1 A_l)) that the device cycle -- CSR SpMV + the 4th-kind Chebyshev
+ * smoother, both already in this library -- will run on.  Rows holding only their diagonal
+ * (Dirichlet rows) stay out of the hierarchy. */
+int pmgx_amg_setup_h(int n_rows, const int32_t* row_ptr_h, const int32_t* cols_h, const double* values_h,
+                     int min_coarse, int max_levels, pmgx_amg_hier** out);
+int pmgx_amg_num_levels(pmgx_amg_hier* h);
+/* out_h[0] = rows of A_l, [1] = nnz(A_l), [2] = columns of P_l (0 on the coarsest level), [3] = nnz(P_l) */
+int pmgx_amg_level_sizes(pmgx_amg_hier* h, int level, long long* out_h);
+int pmgx_amg_level_get(pmgx_amg_hier* h, int level, int32_t* a_ptr_h, int32_t* a_cols_h, double* a_vals_h,
+                       int32_t* p_ptr_h, int32_t* p_cols_h, double* p_vals_h, double* lmax_h);
+int pmgx_amg_destroy(pmgx_amg_hier* h);
 
 /* ------------------------------------------------------------------ V-cycle -- */
 /* MultigridPreconditioner (src/pmg.hpp:22-155). Level 0 is the coarsest.  ops[n_levels],
