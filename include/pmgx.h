@@ -161,6 +161,8 @@ int pmgx_laplacian_create(pmgx_ctx* ctx, int degree, int n_cells, const int32_t*
 int pmgx_laplacian_get_G(pmgx_operator* op, double* G_out);
 /* 1 when the operator runs the affine-geometry kernel (all cells affine, no PMGX_LAP_STREAM_G) */
 int pmgx_laplacian_is_affine(pmgx_operator* op);
+/* name and template arguments of the apply kernel this operator launches (for bench / profiles) */
+int pmgx_laplacian_kernel_name(pmgx_operator* op, char* name_h, int cap);
 
 /* ------------------------------------------------------------- CSR operator -- */
 /* MatrixOperator (src/csr.hpp:57-131): row_ptr[n_rows+1], off_diag_offset[n_rows] (first

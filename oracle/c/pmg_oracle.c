@@ -33,6 +33,18 @@ int orc_num_threads(void)
 #endif
 }
 
+/* the launcher may have exported OMP_NUM_THREADS=1 (torch.distributed.run does): the timed CPU arm
+ * sets the thread count explicitly */
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+  if (n > 0)
+    omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* G[c][q][6] (reference layout), detj[c][q]; pts/w1: 1-D GLL points/weights, n = P+1 */
 void orc_geometry(int n, const double* pts, const double* w1, const double* xgeom,
                   const int32_t* geom_dofmap, int64_t ncells, double* G, double* detj)

@@ -21,6 +21,7 @@ def _load():
     L = ctypes.CDLL(_SO)
     vp, i64, dbl, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_double, ctypes.c_int
     L.orc_num_threads.restype = i32
+    L.orc_set_num_threads.argtypes = [i32]
     L.orc_geometry.argtypes = [i32, vp, vp, vp, vp, i64, vp, vp]
     L.orc_apply.argtypes = [i32, vp, vp, vp, vp, vp, i64, i64, vp, vp]
     L.orc_spmv.argtypes = [i64, vp, vp, vp, vp, vp]
@@ -39,6 +40,11 @@ def _p(a):
 
 def num_threads():
     return int(L.orc_num_threads())
+
+
+def set_num_threads(n):
+    """Explicit OpenMP thread count (torch.distributed.run exports OMP_NUM_THREADS=1)."""
+    L.orc_set_num_threads(int(n))
 
 
 def geometry(verts, geom_dofmap, P):

@@ -297,6 +297,11 @@ class MatFreeLaplacian(_Operator):
         """True when the apply runs the affine-geometry kernel (one geometry 6-vector per cell)."""
         return bool(lib.pmgx_laplacian_is_affine(self.h))
 
+    def kernel_name(self):
+        buf = ctypes.create_string_buffer(96)
+        check(lib.pmgx_laplacian_kernel_name(self.h, ctypes.addressof(buf), 96))
+        return buf.value.decode()
+
     def geometry_factors(self):
         nq = (self.degree + 1) ** 3
         G = self.ctx.zeros(self.n_list * nq * 6)
@@ -486,7 +491,7 @@ class MultigridPreconditioner:
         ops = P(*[o.h for o in self.operators])
         sm = P(*[s.h for s in self.solvers])
         bcs = P(*[ptr(b) for b in self.bc_markers])
-        its = (ctypes.c_void_p * max(nl - 1, 1))(*[i.h for i in self.interpolators])
+        its = (ctypes.c_void_p * max(nl - 1, 1))(*[i.h for i in (self.interpolators or [])])
         h = ctypes.c_void_p()
         check(lib.pmgx_vcycle_create(self.ctx.h, nl, ctypes.addressof(ops), ctypes.addressof(sm),
                                      ctypes.addressof(its), ctypes.addressof(bcs),

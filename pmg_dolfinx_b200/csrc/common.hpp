@@ -138,6 +138,8 @@ struct pmgx_ctx
   double** d_ar_peers = nullptr;          // device array [nranks]: every rank's ar_local, mapped here
   std::vector<void*> p2p_mapped;          // IPC mappings to close at destroy
   unsigned long long* d_ar_epoch = nullptr; // device counter of completed all-reduces
+  // wall-time bound of the in-kernel waits on peer flags (0 = unbounded); PMGX_P2P_TIMEOUT_S, default 600 s
+  unsigned long long p2p_timeout_ns = 600ull * 1000000000ull;
   long long launches = 0;
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[PMGX_MAX_DEGREE + 1];

@@ -51,13 +51,15 @@ int pmgx_ctx_create(int device, int rank, int nranks, const void* nccl_id_h, pmg
     PMGX_CUDA(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, hi));
   }
   PMGX_CUDA(cudaMalloc(&c->d_scalars, 64 * sizeof(double)));
-  PMGX_CUDA(cudaMemset(c->d_scalars, 0, 64 * sizeof(double)));
+  PMGX_CUDA(cudaMemsetAsync(c->d_scalars, 0, 64 * sizeof(double), c->stream));
   PMGX_CUDA(cudaHostAlloc(&c->h_scalars, 64 * sizeof(double), cudaHostAllocMapped));
   PMGX_CUDA(cudaHostGetDevicePointer(&c->h_scalars_dev, c->h_scalars, 0));
   c->max_red_blocks = 8 * c->num_sms;
   PMGX_CUDA(cudaMalloc(&c->d_partials, (size_t)c->max_red_blocks * 4 * sizeof(double)));
   PMGX_CUDA(cudaMalloc(&c->d_counter, 16 * sizeof(unsigned int)));
-  PMGX_CUDA(cudaMemset(c->d_counter, 0, 16 * sizeof(unsigned int)));
+  PMGX_CUDA(cudaMemsetAsync(c->d_counter, 0, 16 * sizeof(unsigned int), c->stream));
+  // the zero fills must have landed before any kernel on a (non-blocking) stream reads them
+  PMGX_CUDA(cudaStreamSynchronize(c->stream));
   if (nranks > 1)
   {
     ncclUniqueId id;

@@ -87,11 +87,11 @@ k_pack_p2p(int ns, int n_nbr, const int* __restrict__ send_offsets, const int32_
 // behind it in the stream then only runs once the data is here (no spinning CTAs holding SMs
 // that the interior-cell kernel wants).
 __global__ void k_wait_p2p(int n_nbr, const unsigned long long* __restrict__ flags,
-                           const unsigned long long* __restrict__ epoch_ptr)
+                           const unsigned long long* __restrict__ epoch_ptr, unsigned long long timeout_ns)
 {
   const unsigned long long epoch = *epoch_ptr; // the pack kernel before this one has advanced it
   for (int t = threadIdx.x; t < n_nbr; t += blockDim.x)
-    wait_epoch(flags + t, epoch); // traps after ~10 s if a neighbour never arrives
+    wait_epoch(flags + t, epoch, timeout_ns); // bounded in wall time, see reduce.cuh
 }
 
 __global__ void k_unpack_cg(int n, const int32_t* __restrict__ idx, const double* __restrict__ bufs,
@@ -128,7 +128,8 @@ static void halo_fwd_begin_p2p(pmgx_halo* h, double* x, const double* sub)
   if (nr > 0)
   {
     const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(h->xbuf + 2 * (size_t)std::max(nr, 1));
-    k_wait_p2p<<<1, 32, 0, c->comm_stream>>>((int)h->recv_ranks.size(), flags, h->d_epoch.p);
+    k_wait_p2p<<<1, 32, 0, c->comm_stream>>>((int)h->recv_ranks.size(), flags, h->d_epoch.p,
+                                             c->p2p_timeout_ns);
     k_unpack_cg<<<(nr + PT - 1) / PT, PT, 0, c->comm_stream>>>(nr, h->recv_idx.p, h->xbuf, h->d_epoch.p, x + h->n_owned);
     check_launch("k_unpack(p2p)");
     count_launch(c, 2);
@@ -207,7 +208,8 @@ void halo_setup_p2p(pmgx_halo* h)
   std::memset(&hd, 0, sizeof(hd));
   if (ok)
   {
-    ok = cudaMalloc(&h->xbuf, bytes) == cudaSuccess && cudaMemset(h->xbuf, 0, bytes) == cudaSuccess
+    ok = cudaMalloc(&h->xbuf, bytes) == cudaSuccess && cudaMemsetAsync(h->xbuf, 0, bytes, h->ctx->stream) == cudaSuccess
+         && cudaStreamSynchronize(h->ctx->stream) == cudaSuccess
          && cudaIpcGetMemHandle(&hd, h->xbuf) == cudaSuccess;
     cudaGetLastError();
   }

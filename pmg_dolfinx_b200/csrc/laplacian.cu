@@ -1925,6 +1925,22 @@ int pmgx_laplacian_is_affine(pmgx_operator* op)
   return op && op->kind == pmgx_operator::LAPLACIAN && static_cast<Laplacian*>(op)->affine ? 1 : 0;
 }
 
+int pmgx_laplacian_kernel_name(pmgx_operator* op, char* name_h, int cap)
+{
+  PMGX_API_BEGIN
+  PMGX_REQUIRE(op && op->kind == pmgx_operator::LAPLACIAN && name_h && cap > 0, "laplacian_kernel_name: bad arguments");
+  auto* L = static_cast<Laplacian*>(op);
+  if (L->lay.mode == 1 && L->affine)
+    snprintf(name_h, cap, "%s<%d,%d>", L->aff_shfl ? "k_apply_affine_shfl" : "k_apply_affine", L->P, L->tma_tpb);
+  else if (L->lay.mode == 1 && L->use_tma)
+    snprintf(name_h, cap, "k_apply_tma<%d,%d,%d>", L->P, L->tma_tpb, L->tma_r);
+  else if (L->lay.mode == 1)
+    snprintf(name_h, cap, "k_apply_slab<%d>", L->P);
+  else
+    snprintf(name_h, cap, "k_apply<%d>", L->P);
+  PMGX_API_END
+}
+
 int pmgx_laplacian_rhs(pmgx_operator* op, const double* fvals, double g, double* b)
 {
   PMGX_API_BEGIN

@@ -69,6 +69,8 @@ void ctx_setup(pmgx_ctx* c)
   c->p2p = false;
   if (c->nranks == 1)
     return;
+  if (const char* t = getenv("PMGX_P2P_TIMEOUT_S"))
+    c->p2p_timeout_ns = (unsigned long long)(std::max(atof(t), 0.0) * 1e9);
   const char* env = getenv("PMGX_P2P");
   const bool want = !(env && std::strcmp(env, "0") == 0) && c->nranks <= 32;
   const size_t bytes = ((size_t)2 * c->nranks * AR_MAX + c->nranks) * sizeof(double);
@@ -77,7 +79,8 @@ void ctx_setup(pmgx_ctx* c)
   std::memset(&h, 0, sizeof(h));
   if (ok)
   {
-    ok = cudaMalloc(&c->ar_local, bytes) == cudaSuccess && cudaMemset(c->ar_local, 0, bytes) == cudaSuccess
+    ok = cudaMalloc(&c->ar_local, bytes) == cudaSuccess && cudaMemsetAsync(c->ar_local, 0, bytes, c->stream) == cudaSuccess
+         && cudaStreamSynchronize(c->stream) == cudaSuccess
          && cudaIpcGetMemHandle(&h, c->ar_local) == cudaSuccess;
     cudaGetLastError();
   }
@@ -114,7 +117,8 @@ void ctx_setup(pmgx_ctx* c)
     return;
   }
   PMGX_CUDA(cudaMalloc(&c->d_ar_epoch, sizeof(unsigned long long)));
-  PMGX_CUDA(cudaMemset(c->d_ar_epoch, 0, sizeof(unsigned long long)));
+  PMGX_CUDA(cudaMemsetAsync(c->d_ar_epoch, 0, sizeof(unsigned long long), c->stream));
+  PMGX_CUDA(cudaStreamSynchronize(c->stream));
   PMGX_CUDA(cudaMalloc(&c->d_ar_peers, c->nranks * sizeof(double*)));
   PMGX_CUDA(cudaMemcpy(c->d_ar_peers, peers.data(), c->nranks * sizeof(double*), cudaMemcpyHostToDevice));
   c->p2p = true;
@@ -149,6 +153,7 @@ PeerReduce next_epoch(pmgx_ctx* c)
     pr.myrank = c->rank;
     pr.nranks = c->nranks;
     pr.epoch_ptr = c->d_ar_epoch;
+    pr.timeout_ns = c->p2p_timeout_ns;
   }
   return pr;
 }

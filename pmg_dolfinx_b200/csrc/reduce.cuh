@@ -22,6 +22,7 @@ struct PeerReduce
   // device counter of completed all-reduces: the kernel takes *epoch_ptr + 1 and stores it back,
   // so a launch carries no per-call state and can be replayed from a CUDA graph
   unsigned long long* epoch_ptr = nullptr;
+  unsigned long long timeout_ns = 0; // 0: wait for ever (like NCCL); else trap after this long (wait_epoch)
 };
 
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v)
@@ -34,15 +35,28 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-// spin until *p >= epoch; a peer that never arrives (crashed rank) traps after ~10 s instead of
-// hanging the GPU
-__device__ __forceinline__ void wait_epoch(const unsigned long long* p, unsigned long long epoch)
+__device__ __forceinline__ unsigned long long globaltimer_ns()
 {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// spin until *p >= epoch.  Benign rank skew (a peer busy with host work, a first-use graph
+// instantiation, a debugger) must not kill the context, so the wait is bounded in WALL time
+// (%globaltimer), not in polls: timeout_ns = 0 waits for ever like NCCL would; otherwise a peer
+// that has not arrived after timeout_ns (default 10 min, PMGX_P2P_TIMEOUT_S) is taken for dead
+// and the kernel traps instead of hanging the GPU.
+__device__ __forceinline__ void wait_epoch(const unsigned long long* p, unsigned long long epoch,
+                                           unsigned long long timeout_ns)
+{
+  if (ld_acquire_sys_u64(p) >= epoch)
+    return;
+  const unsigned long long t0 = globaltimer_ns();
   unsigned int spins = 0;
   while (ld_acquire_sys_u64(p) < epoch)
   {
-    __nanosleep(64);
-    if (++spins > (1u << 27))
+    __nanosleep(spins < 64 ? 32 : 256);
+    if ((++spins & 1023u) == 0 && timeout_ns != 0 && globaltimer_ns() - t0 > timeout_ns)
       __trap();
   }
 }
@@ -63,7 +77,7 @@ __device__ __forceinline__ void peer_allreduce(const PeerReduce& pr, const doubl
       dst[k] = vals[k];
     __threadfence_system();
     st_release_sys_u64(reinterpret_cast<unsigned long long*>(pr.peers[r] + flag_off) + pr.myrank, epoch);
-    wait_epoch(reinterpret_cast<const unsigned long long*>(pr.peers[pr.myrank] + flag_off) + r, epoch);
+    wait_epoch(reinterpret_cast<const unsigned long long*>(pr.peers[pr.myrank] + flag_off) + r, epoch, pr.timeout_ns);
   }
   __syncthreads();
   if (r < count)

@@ -1,10 +1,11 @@
-"""Multi-GPU parity check (run under torchrun, one rank per GPU).
+"""Multi-GPU parity check (run under torchrun, one rank per GPU; also called in-process by bench.py
+before its timed region).
 
 Partitions a small box mesh over the ranks with the product's host partitioner, runs the
-operator apply, Jacobi-CG, Chebyshev and the P4->P2->P1 V-cycle with NCCL halo exchange and
-all-reduced dots, gathers the owned values on rank 0 and compares them with the single-domain
-oracle in the canonical global numbering (result must be partition independent to
-1e-12; histories 1e-10, identical CG iteration counts).  Exit code 0 = pass.
+operator apply, Jacobi-CG, Chebyshev and the P4->P2->P1 V-cycle with the peer-memory / NCCL halo
+exchange and all-reduced dots, gathers the owned values on rank 0 and compares them with the
+single-domain oracle in the canonical global numbering (result must be partition
+independent to 1e-12; histories 1e-10, identical CG iteration counts).  Exit code 0 = pass.
 """
 import os
 import sys
@@ -28,6 +29,19 @@ def main():
     ctx = api.Context(local, rank, world, box[0])
     n = tuple(int(v) for v in os.environ.get("PMGX_CHECK_MESH", "9,8,7").split(","))
     perturb = float(os.environ.get("PMGX_CHECK_PERTURB", "0.15"))
+    res = run_check(api, ctx, rank, world, n, perturb)
+    ctx.sync()
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print(f"[mgpu x{world}] {'PASS' if res['ok'] else 'FAIL'} (max rel err / tolerance = {res['max_err_over_tol']:.3e})",
+              flush=True)
+    sys.exit(0 if res["ok"] else 1)
+
+
+def run_check(api, ctx, rank, world, n=(9, 8, 7), perturb=0.15, log=print):
+    """Collective over all ranks of ctx (torch.distributed must be initialised when world > 1).
+    Returns {"ok", "max_rel", "max_err_over_tol", "transport", "checks"} on every rank."""
     degrees = (1, 2, 4)
     mesh = api.BoxMesh(n, PGRID[world], rank, perturb=perturb)
     # the same perturbed geometry for the oracle: take it from a single-domain product mesh
@@ -36,8 +50,11 @@ def main():
     def gather_owned(vec, sp):
         """rank 0 gets the global vector in canonical numbering."""
         vals = vec.data[: sp.n_owned].cpu().numpy() if hasattr(vec, "data") else vec
-        objs = [None] * world if rank == 0 else None
-        dist.gather_object((sp.l2g[: sp.n_owned], vals), objs, dst=0)
+        if world > 1:
+            objs = [None] * world if rank == 0 else None
+            dist.gather_object((sp.l2g[: sp.n_owned], vals), objs, dst=0)
+        else:
+            objs = [(sp.l2g[: sp.n_owned], vals)]
         if rank != 0:
             return None
         out = np.full(sp.n_global, np.nan)
@@ -58,14 +75,17 @@ def main():
     lv = []
     for P in degrees:
         sp = mesh.space(P, want_coords=True)
-        halo = api.Halo.from_space(ctx, sp)
+        halo = api.Halo.from_space(ctx, sp) if world > 1 else None
         dm, bc = ctx.to_device(sp.dofmap), ctx.to_device(sp.bc)
         op = api.MatFreeLaplacian(ctx, P, kappa, dm, xgeom, gdm, mesh.lcells, mesh.bcells, bc, sp.n_owned, sp.n_ghost, halo)
         lv.append(dict(P=P, sp=sp, halo=halo, dm=dm, bc=bc, op=op))
 
-    if rank == 0:
+    transport = "none"
+    if world > 1:
         paths = {bool(api.lib.pmgx_halo_uses_p2p(d["halo"].h)) for d in lv} | {bool(api.lib.pmgx_ctx_uses_p2p(ctx.h))}
-        print("halo path: " + ("nvlink-p2p" if paths == {True} else "nccl" if paths == {False} else "mixed"), flush=True)
+        transport = "nvlink-p2p" if paths == {True} else "nccl" if paths == {False} else "mixed"
+    if rank == 0:
+        log("halo path: " + transport)
 
     # ---------------- oracle on rank 0 (single domain, same geometry)
     ok = True
@@ -80,12 +100,16 @@ def main():
             A = (lambda P, dm, G, kap, bc: lambda v: oo.apply(P, dm, G, kap, bc, v))(P, dm, G, kap, bc)
             O.append(dict(P=P, dm=dm, bc=bc, nd=nd, A=A, dinv=1.0 / oo.diagonal(P, dm, G, kap, bc, nd)))
 
+    checks, worst = {}, [0.0, 0.0]
+
     def check(name, got, ref, tol):
         nonlocal ok
-        err = np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-300)
+        err = float(np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-300))
         good = err <= tol
         ok = ok and good
-        print(f"[mgpu x{world}] {name:38s} rel err {err:.3e}  {'ok' if good else 'FAIL'}", flush=True)
+        checks[name] = err
+        worst[0], worst[1] = max(worst[0], err), max(worst[1], err / tol)
+        log(f"[mgpu x{world}] {name:38s} rel err {err:.3e}  {'ok' if good else 'FAIL'}")
 
     rng = np.random.default_rng(42)
     smoothers, eigs = [], []
@@ -120,7 +144,8 @@ def main():
             check(f"P{P} diag inverse", dg, o["dinv"], 1e-13)
             xo, ko, al, be, ho, r0o = osol.cg(o["A"], o["dinv"], np.zeros(o["nd"]), np.ones(o["nd"]), 20, 1e-6)
             ok = ok and (k == ko)
-            print(f"[mgpu x{world}] P{P} CG iterations {k} vs oracle {ko}", flush=True)
+            checks[f"P{P} CG iterations (ours, oracle)"] = [int(k), int(ko)]
+            log(f"[mgpu x{world}] P{P} CG iterations {k} vs oracle {ko}")
             check(f"P{P} CG residual history", hist, ho, 1e-10)
             check(f"P{P} CG solution", xsg, xo, 1e-9)
             check(f"P{P} lambda_max", np.array([eig[-1]]), np.array([osol.lanczos_eigenvalues(al, be)[-1]]), 1e-9)
@@ -172,16 +197,16 @@ def main():
             hov = np.array([h[2] for h in ho])
             good = len(hg) == len(hov) and np.all(np.abs(hg - hov) <= 1e-9 * hov[0])
             ok = ok and good
-            print(f"[mgpu x{world}] V-cycle {it} stage residuals {'ok' if good else 'FAIL'} (final {rn:.6e} vs {hov[-1]:.6e})", flush=True)
+            log(f"[mgpu x{world}] V-cycle {it} stage residuals {'ok' if good else 'FAIL'} (final {rn:.6e} vs {hov[-1]:.6e})")
             check(f"V-cycle {it} solution", ug, uo, 1e-9)
-    flag = torch.tensor([1 if ok else 0], device=ctx.device)
-    dist.broadcast(flag, src=0)
+    res = [dict(ok=bool(ok), max_rel=worst[0], max_err_over_tol=worst[1], transport=transport, checks=checks,
+                mesh=list(n), perturb=perturb) if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(res, src=0)
     ctx.sync()
-    dist.barrier()
-    dist.destroy_process_group()
-    if rank == 0:
-        print(f"[mgpu x{world}] {'PASS' if ok else 'FAIL'}", flush=True)
-    sys.exit(0 if int(flag.item()) == 1 else 1)
+    full.close()
+    mesh.close()
+    return res[0]
 
 
 if __name__ == "__main__":
