@@ -232,7 +232,7 @@ def build_problem(ctx, api, torch, mesh, halos_on):
                                         a["sp"].n_owned + a["sp"].n_ghost, b["sp"].n_owned + b["sp"].n_ghost,
                                         mesh.lcells, mesh.bcells, a["halo"], b["halo"]))
     A0 = ops[0].to_csr()
-    coarse = api.CoarseSolverType(ctx, A0, COARSE_ITS, COARSE_RTOL)
+    coarse = api.CoarseSolverType(ctx, A0, COARSE_ITS, COARSE_RTOL, amg=not os.environ.get("PMGX_BENCH_JACOBI_COARSE"))
     pmg = api.MultigridPreconditioner(ctx, [d["bc"] for d in lv])
     pmg.set_solvers(smoothers)
     pmg.set_operators(ops)
@@ -525,7 +525,10 @@ def run_gpu(args):
                        "mesh_cells": list(n), "partition": list(PGRID[world]), "dofs_global": nd_global,
                        "dofs_per_level_rank0": [d["sp"].n_owned for d in keep[0]], "degrees": list(DEGREES),
                        "smoother": f"Chebyshev-4 Jacobi, {NSMOOTH} its", "lambda_max": eigs,
-                       "coarse": f"CSR Jacobi-PCG <= {COARSE_ITS} its, rtol {COARSE_RTOL}",
+                       "coarse": (f"CSR PCG <= {COARSE_ITS} its, rtol {COARSE_RTOL} (src/amg.hpp:36-40), preconditioner: "
+                                  + ("smoothed-aggregation V(2,2) cycle, Chebyshev-4/Jacobi smoother" if keep[5].amg else "Jacobi")),
+                       "coarse_levels_rank0": keep[5].levels(), "coarse_converged_last_cycle": keep[5].last_status()[0],
+                       "coarse_rel_residual_last_cycle": keep[5].last_status()[1],
                        "l2": "working set >> 126 MB L2, no flush needed",
                        "coarse_iterations_last_cycle": int(api.lib.pmgx_coarse_last_iterations(keep[5].h)),
                        "halo": "nvlink-p2p" if api.lib.pmgx_ctx_uses_p2p(ctx.h) else ("nccl" if world > 1 else "none"),

@@ -235,28 +235,64 @@ int pmgx_interp_restrict(pmgx_interp* it, double* fine, double* coarse);  /* rev
 int pmgx_interp_destroy(pmgx_interp* it);
 
 /* ------------------------------------------------------------ coarse solver -- */
-/* CoarseSolverType::solve(x, b) (src/amg.hpp:67-113; PETSc CG + BoomerAMG there): here
- * Jacobi-PCG on the assembled CSR operator (north_star item 5), <= max_iter iterations,
- * relative tolerance rtol on sqrt(r.M^-1 r). */
+/* CoarseSolverType::solve(x, b) (src/amg.hpp:67-113; PETSc KSPCG + PCHYPRE/BoomerAMG, maxits 60, PETSc's
+ * default rtol 1e-5 there): PCG on the assembled CSR operator (north_star item 5), <= max_iter
+ * iterations, relative tolerance rtol on sqrt(r.M^-1 r).
+ *   pmgx_coarse_create      M = Jacobi (diag^-1 of the operator)
+ *   pmgx_coarse_create_amg  M = one V(nu,nu) cycle of a smoothed-aggregation hierarchy built from the
+ *                           operator (host set-up pmgx_amg_setup_dist_h, device cycle: this library's CSR
+ *                           SpMV + 4th-kind Chebyshev/Jacobi smoother, rank-local CSR transfers, dense
+ *                           inverse of the gathered coarsest level).  COLLECTIVE with nranks > 1 (it
+ *                           creates one halo plan per level).  min_coarse / max_levels <= 0: defaults. */
 int pmgx_coarse_create(pmgx_ctx* ctx, pmgx_operator* A_csr, int max_iter, double rtol,
                        pmgx_coarse** out);
+int pmgx_coarse_create_amg(pmgx_ctx* ctx, pmgx_operator* A_csr, int max_iter, double rtol, int nu,
+                           int min_coarse, int max_levels, pmgx_coarse** out);
 int pmgx_coarse_solve(pmgx_coarse* cs, double* x, const double* b, int* iters_h);
 /* iterations of the most recent solve (stand-alone or inside pmgx_vcycle_apply); the host looks at
- * the residual every 8 iterations, so the count is a multiple of 8 or max_iter */
+ * the residual every 8 (Jacobi) / 2 (AMG) iterations, so the count is a multiple of that or max_iter */
 int pmgx_coarse_last_iterations(pmgx_coarse* cs);
+/* did the most recent solve reach rtol (1) or stop at max_iter (0); relative residual
+ * sqrt(r.M^-1 r / r0.M^-1 r0) at the last host check.  Non-convergence is never silent. */
+int pmgx_coarse_last_status(pmgx_coarse* cs, int* converged_h, double* rel_residual_h);
+/* levels of the AMG hierarchy (1 for Jacobi) and, per level, out_h[0]=owned rows [1]=nnz(A_l)
+ * [2]=ghosts [3]=1 if dense coarsest solve; operator complexity = sum nnz / nnz(A_0) */
+int pmgx_coarse_num_levels(pmgx_coarse* cs);
+int pmgx_coarse_level_info(pmgx_coarse* cs, int level, long long* out_h);
+/* one application of the preconditioner alone, u = M^-1 r (for tests) */
+int pmgx_coarse_apply_preconditioner(pmgx_coarse* cs, const double* r, double* u);
 int pmgx_coarse_destroy(pmgx_coarse* cs);
 
 /* ------------------------------------- multilevel coarse solver: host set-up -- */
-/* First half of the smoothed-aggregation coarse solver that is to stand where the reference runs
- * PETSc CG + BoomerAMG (src/amg.hpp:33-47).  Pure host code, no GPU needed, single-rank matrices
- * (every column owned).  NOT yet used by pmgx_coarse_solve / the V-cycle: it builds the hierarchy
- * (A_l, P_l, lambda_max(D^-1 A_l)) that the device cycle -- CSR SpMV + the 4th-kind Chebyshev
- * smoother, both already in this library -- will run on.  Rows holding only their diagonal
- * (Dirichlet rows) stay out of the hierarchy. */
+/* Set-up of the smoothed-aggregation hierarchy that pmgx_coarse_create_amg runs on the device, where
+ * the reference runs PETSc CG + BoomerAMG (src/amg.hpp:33-47).  Pure host code, no GPU needed;
+ * exported so that the hierarchy (A_l, P_l, lambda_max(D^-1 A_l), halo plans) can be inspected and
+ * tested on the CPU.  Rows holding only their diagonal (Dirichlet rows) stay out of the hierarchy.
+ * _setup_h: single rank (every column owned).  _setup_dist_h: COLLECTIVE over nranks ranks; rows are
+ * this rank's owned dofs, columns >= n_owned address the ghosts of the forward-scatter plan given in
+ * the pmgx_halo_create format; `allgather(user, mine, bytes, all)` must gather `bytes` bytes of every
+ * rank into all[rank * bytes ...] and return 0 (the only collective the set-up uses).  Aggregates never
+ * span ranks and the prolongator is smoothed with the rank-local part of A, so P_l is rank-local. */
+typedef int (*pmgx_allgather_fn)(void* user, const void* mine, size_t bytes, void* all);
 int pmgx_amg_setup_h(int n_rows, const int32_t* row_ptr_h, const int32_t* cols_h, const double* values_h,
                      int min_coarse, int max_levels, pmgx_amg_hier** out);
+int pmgx_amg_setup_dist_h(int rank, int nranks, int n_owned, int n_ghost, const int32_t* row_ptr_h,
+                          const int32_t* cols_h, const double* values_h, int n_send_nbr, const int* send_ranks_h,
+                          const int* send_offsets_h, const int32_t* send_idx_h, int n_recv_nbr,
+                          const int* recv_ranks_h, const int* recv_offsets_h, const int32_t* recv_idx_h,
+                          pmgx_allgather_fn allgather, void* user, int min_coarse, int max_levels,
+                          pmgx_amg_hier** out);
+/* out_h[0]=n_owned [1]=n_ghost [2]=n_send_nbr [3]=n_send [4]=n_recv_nbr [5]=n_recv
+ * [6]=1 if this (coarsest) level holds rows of the dense inverse [7]=global rows of the level */
+int pmgx_amg_level_dist_sizes(pmgx_amg_hier* h, int level, long long* out_h);
+/* ghost_src_h/ghost_rid_h[n_ghost]: owner rank and owner-local index of every ghost; halo plan of the
+ * level; inv_rows_h[n_owned * n_global]: this rank's rows of the inverse of the gathered coarsest
+ * matrix, columns ordered [owned | other ranks' entries in rank order].  Any pointer may be NULL. */
+int pmgx_amg_level_dist_get(pmgx_amg_hier* h, int level, int* ghost_src_h, int32_t* ghost_rid_h, int* send_ranks_h,
+                            int* send_offsets_h, int32_t* send_idx_h, int* recv_ranks_h, int* recv_offsets_h,
+                            int32_t* recv_idx_h, double* inv_rows_h);
 int pmgx_amg_num_levels(pmgx_amg_hier* h);
-/* out_h[0] = rows of A_l, [1] = nnz(A_l), [2] = columns of P_l (0 on the coarsest level), [3] = nnz(P_l) */
+/* out_h[0] = (owned) rows of A_l, [1] = nnz(A_l), [2] = columns of P_l (0 on the coarsest level), [3] = nnz(P_l) */
 int pmgx_amg_level_sizes(pmgx_amg_hier* h, int level, long long* out_h);
 int pmgx_amg_level_get(pmgx_amg_hier* h, int level, int32_t* a_ptr_h, int32_t* a_cols_h, double* a_vals_h,
                        int32_t* p_ptr_h, int32_t* p_cols_h, double* p_vals_h, double* lmax_h);

@@ -494,17 +494,21 @@ private:
   pmgx_interp* _h = nullptr;
 };
 
-/// Coarse solver hook (src/amg.hpp:10-118: PETSc CG + BoomerAMG there): Jacobi-PCG on the
-/// assembled CSR operator (north_star item 5).
+/// Coarse solver hook (src/amg.hpp:10-118: PETSc KSPCG + BoomerAMG, maxits 60, rtol 1e-5 there): PCG on
+/// the assembled CSR operator (north_star item 5) preconditioned by a smoothed-aggregation V(2,2)
+/// cycle (amg = true, collective over the ranks) or by Jacobi.
 template <typename T>
 class CoarseSolverType
 {
 public:
   CoarseSolverType(std::shared_ptr<dolfinx::acc::MatrixOperator<T>> A, std::shared_ptr<const pmgx::IndexMap> map,
-                   int max_iterations = 60, double rtol = 1e-5)
+                   int max_iterations = 60, double rtol = 1e-5, bool amg = true)
       : _A(A)
   {
-    pmgx::check(pmgx_coarse_create(map->ctx()->handle(), A->handle(map), max_iterations, rtol, &_h));
+    if (amg)
+      pmgx::check(pmgx_coarse_create_amg(map->ctx()->handle(), A->handle(map), max_iterations, rtol, 2, 0, 0, &_h));
+    else
+      pmgx::check(pmgx_coarse_create(map->ctx()->handle(), A->handle(map), max_iterations, rtol, &_h));
   }
   ~CoarseSolverType() { pmgx_coarse_destroy(_h); }
   template <typename Vector>

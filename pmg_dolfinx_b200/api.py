@@ -450,18 +450,45 @@ class Interpolator:
 
 
 class CoarseSolverType:
-    """CoarseSolverType<T>::solve(x, b) (src/amg.hpp:67-113) backed by CSR Jacobi-PCG."""
+    """CoarseSolverType<T>::solve(x, b) (src/amg.hpp:67-113: PETSc KSPCG + BoomerAMG, maxits 60, rtol 1e-5):
+    PCG on the assembled CSR operator, preconditioned by one V(nu,nu) cycle of a smoothed-aggregation
+    hierarchy (amg=True, the default; collective over the ranks) or by Jacobi (amg=False)."""
 
-    def __init__(self, ctx, A_csr, max_iter=60, rtol=1e-10):
-        self.ctx, self.A = ctx, A_csr
+    def __init__(self, ctx, A_csr, max_iter=60, rtol=1e-5, amg=True, nu=2, min_coarse=0, max_levels=0):
+        self.ctx, self.A, self.amg = ctx, A_csr, bool(amg)
         h = ctypes.c_void_p()
-        check(lib.pmgx_coarse_create(ctx.h, A_csr.h, int(max_iter), float(rtol), ctypes.addressof(h)))
+        if amg:
+            check(lib.pmgx_coarse_create_amg(ctx.h, A_csr.h, int(max_iter), float(rtol), int(nu), int(min_coarse),
+                                             int(max_levels), ctypes.addressof(h)))
+        else:
+            check(lib.pmgx_coarse_create(ctx.h, A_csr.h, int(max_iter), float(rtol), ctypes.addressof(h)))
         self.h = h
 
     def solve(self, x, b):
         k = ctypes.c_int()
         check(lib.pmgx_coarse_solve(self.h, ptr(x.data), ptr(b.data), ctypes.addressof(k)))
         return k.value
+
+    def last_iterations(self):
+        return int(lib.pmgx_coarse_last_iterations(self.h))
+
+    def last_status(self):
+        """(converged, relative residual sqrt(r.M^-1 r / r0.M^-1 r0) at the last host check)"""
+        c, r = ctypes.c_int(), ctypes.c_double()
+        check(lib.pmgx_coarse_last_status(self.h, ctypes.addressof(c), ctypes.addressof(r)))
+        return bool(c.value), r.value
+
+    def levels(self):
+        """[(owned rows, nnz, ghosts, dense coarsest?)] of the hierarchy on this rank"""
+        out = []
+        for l in range(lib.pmgx_coarse_num_levels(self.h)):
+            v = np.zeros(4, dtype=np.int64)
+            check(lib.pmgx_coarse_level_info(self.h, l, ptr(v)))
+            out.append(tuple(int(t) for t in v))
+        return out
+
+    def apply_preconditioner(self, r, u):
+        check(lib.pmgx_coarse_apply_preconditioner(self.h, ptr(r.data), ptr(u.data)))
 
 
 class MultigridPreconditioner:

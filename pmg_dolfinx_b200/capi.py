@@ -28,7 +28,7 @@ _SCALARS = {
 
 def _ctype(decl):
     decl = decl.replace("const ", "").strip()
-    if "*" in decl:
+    if "*" in decl or decl.split(" ")[0].endswith("_fn"):  # pointers and callback typedefs
         return ctypes.c_void_p
     base = decl.rsplit(" ", 1)[0].strip() if " " in decl and decl not in _SCALARS else decl
     for k in ("long long", "uint64_t", "double", "size_t", "int"):

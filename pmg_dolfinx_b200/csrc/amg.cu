@@ -1,0 +1,368 @@
+// Device cycle of the smoothed-aggregation coarse solver: the preconditioner of the coarse PCG behind
+// CoarseSolverType::solve, where the reference runs PETSc KSPCG + BoomerAMG (src/amg.hpp:33-47,67-113).
+//
+// The hierarchy comes from amg_setup.cpp (host, collective).  Everything the cycle runs already exists
+// in this library: the CSR SpMV with its owned/ghost column split and overlapped halo (csr.cu), the
+// 4th-kind Chebyshev/Jacobi smoother with its dead-iteration elimination (solvers.cu), the
+// peer-memory halo (halo.cu).  Prolongation and restriction are rank-local rectangular CSR products
+// (P and an explicitly stored P^T: a gather, so the restriction is deterministic); the coarsest level
+// is gathered with an all-to-all halo plan and multiplied by this rank's rows of the dense inverse.
+// One V(nu,nu) cycle: per level 2 nu SpMVs + 2 transfers, no host synchronisation anywhere, so the
+// coarse PCG captures whole iterations into a CUDA graph (solvers.cu, cgcg_solve).
+#include "common.hpp"
+#include "operator.hpp"
+#include "csr.hpp"
+#include "solvers.hpp"
+#include "amg.hpp"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+namespace pmgx
+{
+namespace
+{
+// x[row] = sum_c inv[row][c] * b[c]; one warp per row, b = [owned | gathered] (n_cols entries)
+__global__ void __launch_bounds__(256)
+k_dense_rows(int n_rows, int n_cols, const double* __restrict__ inv, const double* __restrict__ b,
+             double* __restrict__ x)
+{
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= n_rows)
+    return;
+  const double* r = inv + (size_t)row * n_cols;
+  double s = 0.0;
+  for (int c = lane; c < n_cols; c += 32)
+    s = fma(r[c], b[c], s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0)
+    x[row] = s;
+}
+
+struct RectCsr
+{
+  int n_rows = 0;
+  DevBuf<int32_t> ptr, cols;
+  DevBuf<double> vals;
+  void upload(const amg::Csr& M, cudaStream_t st)
+  {
+    n_rows = M.n_rows;
+    ptr.upload(M.ptr.data(), M.ptr.size(), st);
+    cols.upload(M.cols.data(), M.cols.size(), st);
+    vals.upload(M.vals.data(), M.vals.size(), st);
+  }
+};
+
+amg::Csr transpose_host(const amg::Csr& A)
+{
+  amg::Csr T;
+  T.n_rows = A.n_cols;
+  T.n_cols = A.n_rows;
+  T.ptr.assign((size_t)A.n_cols + 1, 0);
+  for (int32_t c : A.cols)
+    ++T.ptr[c + 1];
+  for (size_t i = 1; i < T.ptr.size(); ++i)
+    T.ptr[i] += T.ptr[i - 1];
+  T.cols.resize(A.cols.size());
+  T.vals.resize(A.vals.size());
+  std::vector<int32_t> next(T.ptr.begin(), T.ptr.end() - 1);
+  for (int i = 0; i < A.n_rows; ++i)
+    for (int32_t j = A.ptr[i]; j < A.ptr[i + 1]; ++j)
+    {
+      const int32_t p = next[A.cols[j]]++;
+      T.cols[p] = i;
+      T.vals[p] = A.vals[j];
+    }
+  return T;
+}
+
+pmgx_halo* make_halo(pmgx_ctx* c, int n_owned, int n_ghost, const amg::Plan& p)
+{
+  if (c->nranks == 1)
+    return nullptr;
+  pmgx_halo* h = nullptr;
+  const int rc = pmgx_halo_create(c, n_owned, n_ghost, (int)p.send_ranks.size(), p.send_ranks.data(), p.send_offsets.data(),
+                                  p.send_idx.data(), (int)p.recv_ranks.size(), p.recv_ranks.data(), p.recv_offsets.data(),
+                                  p.recv_idx.data(), &h);
+  if (rc != PMGX_OK)
+    throw Error{rc};
+  return h;
+}
+
+struct AmgPrecond : Precond
+{
+  struct Lv
+  {
+    int n_owned = 0, n_ghost = 0;
+    long long nnz = 0;
+    pmgx_operator* A = nullptr;
+    bool own_A = false;
+    pmgx_halo* halo = nullptr; // owned (levels >= 1)
+    pmgx_cheb* sm = nullptr;
+    RectCsr P, R;              // to / from the next coarser level
+    DevBuf<double> x, b;       // levels >= 1 (and the private b of a dense level)
+    bool dense = false;
+    int n_global = 0;
+    DevBuf<double> inv;
+    pmgx_halo* gather = nullptr; // owned
+  };
+  pmgx_ctx* ctx = nullptr;
+  std::vector<Lv> lv;
+  int nu = 2;
+
+  ~AmgPrecond() override
+  {
+    for (Lv& L : lv)
+    {
+      if (L.sm)
+        pmgx_cheb_destroy(L.sm);
+      if (L.own_A && L.A)
+        pmgx_operator_destroy(L.A);
+      if (L.halo)
+        pmgx_halo_destroy(L.halo);
+      if (L.gather)
+        pmgx_halo_destroy(L.gather);
+    }
+  }
+
+  void cycle(int l, const double* b, double* x)
+  {
+    Lv& L = lv[l];
+    if (l + 1 == (int)lv.size())
+    {
+      if (L.dense)
+      {
+        double* bb = L.b.p; // private: its ghost block receives the other ranks' entries
+        if (b != bb)
+          vec::copy(ctx, bb, b, L.n_owned);
+        if (L.gather)
+        {
+          halo_fwd_begin(L.gather, bb);
+          halo_fwd_end(L.gather, bb);
+        }
+        if (L.n_owned > 0)
+        {
+          k_dense_rows<<<(L.n_owned * 32 + 255) / 256, 256, 0, ctx->stream>>>(L.n_owned, L.n_global, L.inv.p, bb, x);
+          check_launch("k_dense_rows");
+          count_launch(ctx);
+        }
+      }
+      else // no dense inverse (level too large): smooth instead
+        cheb_solve(L.sm, L.A, x, b, nullptr, true, CHEB_R_NONE);
+      return;
+    }
+    Lv& C = lv[l + 1];
+    cheb_solve(L.sm, L.A, x, b, nullptr, true, CHEB_R_FULL);          // pre-smoothing from x = 0; sm->r = b - A x
+    spmv_rect(ctx, C.n_owned, L.R.ptr.p, L.R.cols.p, L.R.vals.p, L.sm->r.p, C.b.p, false, 32); // b_c = P^T r
+    cycle(l + 1, C.b.p, C.x.p);
+    spmv_rect(ctx, L.n_owned, L.P.ptr.p, L.P.cols.p, L.P.vals.p, C.x.p, x, true, 8);         // x += P x_c
+    cheb_solve(L.sm, L.A, x, b, nullptr, false, CHEB_R_NONE);         // post-smoothing (same polynomial: M is symmetric)
+  }
+
+  void apply(const double* r, double* u) override { cycle(0, r, u); }
+};
+
+// forward-scatter plan of an existing halo, back on the host
+amg::Plan plan_of(pmgx_halo* h)
+{
+  amg::Plan p;
+  if (!h)
+    return p;
+  p.send_ranks = h->send_ranks;
+  p.send_offsets = h->send_offsets;
+  p.recv_ranks = h->recv_ranks;
+  p.recv_offsets = h->recv_offsets;
+  if (p.send_offsets.empty())
+    p.send_offsets.assign(1, 0);
+  if (p.recv_offsets.empty())
+    p.recv_offsets.assign(1, 0);
+  p.send_idx.resize((size_t)h->n_send());
+  p.recv_idx.resize((size_t)h->n_recv());
+  if (!p.send_idx.empty())
+    PMGX_CUDA(cudaMemcpy(p.send_idx.data(), h->send_idx.p, p.send_idx.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (!p.recv_idx.empty())
+    PMGX_CUDA(cudaMemcpy(p.recv_idx.data(), h->recv_idx.p, p.recv_idx.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  return p;
+}
+} // namespace
+} // namespace pmgx
+
+using pmgx::AmgPrecond;
+
+extern "C"
+{
+int pmgx_coarse_create_amg(pmgx_ctx* ctx, pmgx_operator* A, int max_iter, double rtol, int nu, int min_coarse,
+                           int max_levels, pmgx_coarse** out)
+{
+  PMGX_API_BEGIN
+  PMGX_REQUIRE(ctx && A && out && max_iter >= 0, "coarse_create_amg: bad arguments");
+  PMGX_REQUIRE(A->kind == pmgx_operator::CSR, "coarse_create_amg: the operator must be an assembled CSR operator");
+  PMGX_REQUIRE(nu >= 1 && nu <= 8, "coarse_create_amg: nu must be in 1..8");
+  PMGX_CUDA(cudaSetDevice(ctx->device));
+  if (min_coarse <= 0)
+    min_coarse = 600;
+  if (max_levels <= 0)
+    max_levels = 12;
+  auto* Ac = static_cast<pmgx::CsrOperator*>(A);
+  PMGX_REQUIRE(ctx->nranks == 1 || Ac->halo || Ac->n_ghost == 0, "coarse_create_amg: the operator has ghosts but no halo");
+  // level-0 matrix and its halo plan, back on the host; rows sorted by column for the set-up
+  pmgx::amg::Csr A0;
+  A0.ptr.resize((size_t)Ac->n_owned + 1);
+  A0.cols.resize((size_t)Ac->nnz);
+  A0.vals.resize((size_t)Ac->nnz);
+  {
+    const int rc = pmgx_csr_get(A, A0.ptr.data(), A0.cols.data(), A0.vals.data());
+    if (rc != PMGX_OK)
+      return rc;
+    std::vector<std::pair<int32_t, double>> row;
+    for (int i = 0; i < Ac->n_owned; ++i)
+    {
+      bool sorted = true;
+      for (int32_t j = A0.ptr[i] + 1; j < A0.ptr[i + 1] && sorted; ++j)
+        sorted = A0.cols[j - 1] < A0.cols[j];
+      if (sorted)
+        continue;
+      row.clear();
+      for (int32_t j = A0.ptr[i]; j < A0.ptr[i + 1]; ++j)
+        row.emplace_back(A0.cols[j], A0.vals[j]);
+      std::sort(row.begin(), row.end());
+      for (size_t t = 0; t < row.size(); ++t)
+        A0.cols[A0.ptr[i] + t] = row[t].first, A0.vals[A0.ptr[i] + t] = row[t].second;
+    }
+  }
+  const pmgx::amg::Plan plan0 = pmgx::plan_of(Ac->halo);
+  pmgx::amg::Comm cm;
+  cm.rank = ctx->rank;
+  cm.nranks = ctx->nranks;
+  cm.allgather = [ctx](const void* mine, size_t bytes, void* all)
+  {
+    std::vector<char> buf;
+    pmgx::p2p::allgather_bytes(ctx, mine, bytes, buf);
+    std::memcpy(all, buf.data(), bytes * (size_t)ctx->nranks);
+  };
+  pmgx::amg::Hierarchy H;
+  pmgx::amg::setup(H, std::move(A0), Ac->n_owned, Ac->n_ghost, plan0, cm, min_coarse, max_levels);
+
+  std::unique_ptr<AmgPrecond> M(new AmgPrecond());
+  M->ctx = ctx;
+  M->nu = nu;
+  const int nl = (int)H.levels.size();
+  M->lv.resize((size_t)nl);
+  for (int l = 0; l < nl; ++l)
+  {
+    pmgx::amg::Level& L = H.levels[l];
+    AmgPrecond::Lv& D = M->lv[l];
+    D.n_owned = L.n_owned;
+    D.n_ghost = L.n_ghost;
+    D.nnz = L.A.nnz();
+    const bool last = l + 1 == nl;
+    if (l == 0)
+      D.A = A; // the caller's operator and halo
+    else
+    {
+      D.halo = pmgx::make_halo(ctx, L.n_owned, L.n_ghost, L.plan); // collective: same order on every rank
+      std::vector<int32_t> off((size_t)L.n_owned);
+      for (int i = 0; i < L.n_owned; ++i)
+      {
+        int32_t j = L.A.ptr[i];
+        while (j < L.A.ptr[i + 1] && L.A.cols[j] < L.n_owned)
+          ++j;
+        off[i] = j;
+      }
+      const int rc = pmgx_csr_create(ctx, L.n_owned, L.n_ghost, L.A.ptr.data(), off.data(), L.A.cols.data(),
+                                     L.A.vals.data(), D.halo, &D.A);
+      if (rc != PMGX_OK)
+        return rc;
+      D.own_A = true;
+      const size_t nt = (size_t)L.n_owned + L.n_ghost;
+      D.x.alloc(nt);
+      D.b.alloc(nt);
+      if (nt > 0)
+      {
+        PMGX_CUDA(cudaMemsetAsync(D.x.p, 0, nt * sizeof(double), ctx->stream));
+        PMGX_CUDA(cudaMemsetAsync(D.b.p, 0, nt * sizeof(double), ctx->stream));
+      }
+    }
+    {
+      const int rc = pmgx_cheb_create(ctx, L.n_owned, L.n_ghost, 0.1 * L.lmax, L.lmax, &D.sm);
+      if (rc != PMGX_OK)
+        return rc;
+      // a coarsest level that could not be inverted densely is smoothed harder instead
+      D.sm->max_iter = (last && !L.dense) ? 4 * nu : nu;
+    }
+    if (!last)
+    {
+      D.P.upload(L.P, ctx->stream);
+      D.R.upload(pmgx::transpose_host(L.P), ctx->stream);
+    }
+    else if (L.dense)
+    {
+      D.dense = true;
+      D.n_global = (int)L.n_global;
+      D.inv.upload(L.inv_rows.data(), L.inv_rows.size(), ctx->stream);
+      const int n_gather = (int)L.n_global - L.n_owned;
+      D.gather = pmgx::make_halo(ctx, L.n_owned, n_gather, L.gather_plan);
+      const size_t nt = (size_t)L.n_owned + std::max(L.n_ghost, n_gather);
+      D.b.alloc(nt);
+      if (nt > 0)
+        PMGX_CUDA(cudaMemsetAsync(D.b.p, 0, nt * sizeof(double), ctx->stream));
+    }
+  }
+  PMGX_CUDA(cudaStreamSynchronize(ctx->stream));
+
+  pmgx_coarse* cs = nullptr;
+  const int rc = pmgx_coarse_create(ctx, A, max_iter, rtol, &cs);
+  if (rc != PMGX_OK)
+    return rc;
+  cs->M = M.release();
+  cs->check_every = 2;
+  if (const char* e = getenv("PMGX_COARSE_CHECK_EVERY"))
+    cs->check_every = std::max(atoi(e), 1);
+  *out = cs;
+  PMGX_API_END
+}
+
+int pmgx_coarse_num_levels(pmgx_coarse* cs)
+{
+  if (!cs)
+    return -1;
+  return cs->M ? (int)static_cast<AmgPrecond*>(cs->M)->lv.size() : 1;
+}
+
+int pmgx_coarse_level_info(pmgx_coarse* cs, int level, long long* out_h)
+{
+  PMGX_API_BEGIN
+  PMGX_REQUIRE(cs && out_h && level >= 0 && level < pmgx_coarse_num_levels(cs), "coarse_level_info: bad arguments");
+  if (!cs->M)
+  {
+    out_h[0] = cs->A->n_owned;
+    out_h[1] = pmgx_csr_nnz(cs->A);
+    out_h[2] = cs->A->n_ghost;
+    out_h[3] = 0;
+  }
+  else
+  {
+    const AmgPrecond::Lv& L = static_cast<AmgPrecond*>(cs->M)->lv[level];
+    out_h[0] = L.n_owned;
+    out_h[1] = L.nnz;
+    out_h[2] = L.n_ghost;
+    out_h[3] = L.dense ? 1 : 0;
+  }
+  PMGX_API_END
+}
+
+int pmgx_coarse_apply_preconditioner(pmgx_coarse* cs, const double* r, double* u)
+{
+  PMGX_API_BEGIN
+  PMGX_REQUIRE(cs && r && u && r != u, "coarse_apply_preconditioner: bad arguments");
+  PMGX_CUDA(cudaSetDevice(cs->ctx->device));
+  if (cs->M)
+    cs->M->apply(r, u);
+  else
+    pmgx::vec::pointwise_mult(cs->ctx, u, r, cs->A->diag_inv.p, cs->A->n_owned);
+  PMGX_API_END
+}
+}

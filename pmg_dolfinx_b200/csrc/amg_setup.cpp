@@ -1,31 +1,176 @@
-// Host set-up of a smoothed-aggregation hierarchy on an assembled CSR matrix: the first half of the
-// multilevel coarse solver that is to replace Jacobi-PCG behind CoarseSolverType::solve (the reference
-// runs PETSc CG + BoomerAMG there, src/amg.hpp:33-47).  NOT YET USED BY THE V-CYCLE: this file only
-// builds and exposes the level matrices (single rank: every column is owned); the device cycle --
-// SpMV, the 4th-kind Chebyshev smoother and CSR transfer operators, all of which exist in libpmgx --
-// and the distributed Galerkin product come next.  Sized and checked
-// against the numpy prototype scripts/prototype_sa_amg.py (tests/test_amg_setup.py, CPU only).
+// Host set-up of the distributed smoothed-aggregation hierarchy behind CoarseSolverType::solve (the
+// reference runs PETSc CG + BoomerAMG there, src/amg.hpp:33-47).  See amg.hpp for the distribution
+// model.  Pure host code: the only collective is a fixed-size all-gather of bytes handed in by the
+// caller (NCCL in amg.cu, a torch.distributed callback in the CPU tests), everything else is built
+// on it -- this is set-up, run once.
 //
-// Algorithm per level: greedy (Vanek) aggregation on the graph of the free rows (rows that hold
-// only their diagonal -- Dirichlet rows -- stay out of the hierarchy), tentative prolongator T
-// (piecewise constant), lambda_max(D^-1 A) by power iteration (x1.1), P = (I - 4/(3 lmax) D^-1 A) T,
-// A_c = P^T A P with a row-wise hash SpGEMM; recursion stops at min_coarse rows or max_levels.
+// Per level: greedy (Vanek) aggregation on the rank-local graph of the free rows (rows that hold
+// only their diagonal -- Dirichlet rows, src/csr.hpp:84-86 -- stay out of the hierarchy), tentative
+// prolongator T (piecewise constant), lambda_max(D^-1 A) by distributed power iteration (x1.1),
+// P = (I - 4/(3 lmax) D^-1 A_loc) T with A_loc = owned-column block of A, ghost couplings lumped
+// onto the diagonal; exchange of the P rows of the interface dofs; A_c = P^T A [P; P_ghost] by
+// row-wise SpGEMM; coarse halo plan from the ghost aggregates that A_c references.  Recursion stops
+// at min_coarse free rows (globally) or max_levels; the last level is gathered and inverted densely.
+// Sized and checked against scripts/prototype_sa_amg.py (tests/test_amg_setup.py, tests/test_dist_cpu.py).
 #include "common.hpp"
+#include "amg.hpp"
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
+#include <map>
 #include <numeric>
 
+namespace pmgx
+{
+namespace amg
+{
 namespace
 {
-struct Csr
+constexpr long long DENSE_CAP = 4096; // largest coarsest level that is inverted densely
+
+// ------------------------------------------------------------- collectives on the all-gather --
+std::vector<std::vector<char>> allgather_var(const Comm& cm, const std::vector<char>& mine)
 {
-  int n_rows = 0, n_cols = 0;
-  std::vector<int32_t> ptr, cols;
-  std::vector<double> vals;
-  long long nnz() const { return (long long)cols.size(); }
+  std::vector<std::vector<char>> out((size_t)cm.nranks);
+  if (cm.nranks == 1)
+  {
+    out[0] = mine;
+    return out;
+  }
+  long long sz = (long long)mine.size();
+  std::vector<long long> sizes((size_t)cm.nranks, 0);
+  cm.allgather(&sz, sizeof(sz), sizes.data());
+  const size_t mx = (size_t)std::max<long long>(1, *std::max_element(sizes.begin(), sizes.end()));
+  std::vector<char> pad(mx, 0), all(mx * cm.nranks, 0);
+  if (!mine.empty())
+    std::memcpy(pad.data(), mine.data(), mine.size());
+  cm.allgather(pad.data(), mx, all.data());
+  for (int r = 0; r < cm.nranks; ++r)
+    out[r].assign(all.begin() + (size_t)r * mx, all.begin() + (size_t)r * mx + (size_t)sizes[r]);
+  return out;
+}
+
+double allreduce_sum(const Comm& cm, double v)
+{
+  if (cm.nranks == 1)
+    return v;
+  std::vector<double> all((size_t)cm.nranks, 0.0);
+  cm.allgather(&v, sizeof(v), all.data());
+  double s = 0.0;
+  for (double a : all) // rank order: identical on every rank
+    s += a;
+  return s;
+}
+
+long long allreduce_sum(const Comm& cm, long long v)
+{
+  if (cm.nranks == 1)
+    return v;
+  std::vector<long long> all((size_t)cm.nranks, 0);
+  cm.allgather(&v, sizeof(v), all.data());
+  return std::accumulate(all.begin(), all.end(), 0ll);
+}
+
+template <typename T>
+void put(std::vector<char>& b, const T* p, size_t n)
+{
+  const size_t o = b.size();
+  b.resize(o + n * sizeof(T));
+  if (n)
+    std::memcpy(b.data() + o, p, n * sizeof(T));
+}
+template <typename T>
+void put1(std::vector<char>& b, T v)
+{
+  put(b, &v, 1);
+}
+struct Reader
+{
+  const char* p;
+  const char* e;
+  template <typename T>
+  void get(T* out, size_t n)
+  {
+    if (p + n * sizeof(T) > e)
+      throw std::runtime_error("amg set-up: truncated message");
+    if (n)
+      std::memcpy(out, p, n * sizeof(T));
+    p += n * sizeof(T);
+  }
+  template <typename T>
+  T get1()
+  {
+    T v;
+    get(&v, 1);
+    return v;
+  }
 };
 
+// message k goes to rank dests[k]; returns the messages addressed to this rank, sorted by source
+std::vector<std::pair<int, std::vector<char>>> neighbor_exchange(const Comm& cm, const std::vector<int>& dests,
+                                                                 const std::vector<std::vector<char>>& msgs)
+{
+  std::vector<char> blob;
+  put1<int32_t>(blob, (int32_t)dests.size());
+  for (size_t k = 0; k < dests.size(); ++k)
+  {
+    put1<int32_t>(blob, dests[k]);
+    put1<long long>(blob, (long long)msgs[k].size());
+  }
+  for (size_t k = 0; k < dests.size(); ++k)
+    put(blob, msgs[k].data(), msgs[k].size());
+  auto all = allgather_var(cm, blob);
+  std::vector<std::pair<int, std::vector<char>>> out;
+  for (int r = 0; r < cm.nranks; ++r)
+  {
+    Reader rd{all[r].data(), all[r].data() + all[r].size()};
+    const int nm = rd.get1<int32_t>();
+    std::vector<int32_t> d((size_t)nm);
+    std::vector<long long> sz((size_t)nm);
+    for (int k = 0; k < nm; ++k)
+    {
+      d[k] = rd.get1<int32_t>();
+      sz[k] = rd.get1<long long>();
+    }
+    for (int k = 0; k < nm; ++k)
+    {
+      if (d[k] == cm.rank)
+      {
+        std::vector<char> m((size_t)sz[k]);
+        rd.get(m.data(), m.size());
+        out.emplace_back(r, std::move(m));
+      }
+      else
+        rd.p += sz[k];
+    }
+  }
+  return out;
+}
+
+// x[n_owned + slot] <- owner's value (Vector::scatter_fwd on the host)
+void halo_exchange(const Comm& cm, const Plan& pl, int n_owned, std::vector<double>& x)
+{
+  if (cm.nranks == 1)
+    return;
+  std::vector<std::vector<char>> msgs(pl.send_ranks.size());
+  for (size_t k = 0; k < pl.send_ranks.size(); ++k)
+    for (int t = pl.send_offsets[k]; t < pl.send_offsets[k + 1]; ++t)
+      put1<double>(msgs[k], x[pl.send_idx[t]]);
+  auto in = neighbor_exchange(cm, pl.send_ranks, msgs);
+  for (auto& m : in)
+  {
+    const auto it = std::find(pl.recv_ranks.begin(), pl.recv_ranks.end(), m.first);
+    if (it == pl.recv_ranks.end())
+      continue;
+    const size_t k = it - pl.recv_ranks.begin();
+    Reader rd{m.second.data(), m.second.data() + m.second.size()};
+    for (int t = pl.recv_offsets[k]; t < pl.recv_offsets[k + 1]; ++t)
+      x[(size_t)n_owned + pl.recv_idx[t]] = rd.get1<double>();
+  }
+}
+
+// ------------------------------------------------------------------------ sparse kernels --
 // C = A * B, rows sorted by column
 Csr spgemm(const Csr& A, const Csr& B)
 {
@@ -98,11 +243,12 @@ std::vector<double> diagonal(const Csr& A)
 }
 
 // lambda_max(D^-1 A) by power iteration from a fixed pseudo-random start (deterministic)
-double lambda_max(const Csr& A, const std::vector<double>& d, int its)
+double lambda_max(const Level& L, const std::vector<double>& d, const Comm& cm, int its)
 {
-  const int n = A.n_rows;
-  std::vector<double> x((size_t)n), y((size_t)n);
-  unsigned long long s = 0x9E3779B97F4A7C15ull;
+  const Csr& A = L.A;
+  const int n = L.n_owned;
+  std::vector<double> x((size_t)n + L.n_ghost, 0.0), y((size_t)n);
+  unsigned long long s = 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull * (unsigned long long)cm.rank;
   for (int i = 0; i < n; ++i)
   {
     s ^= s << 13, s ^= s >> 7, s ^= s << 17;
@@ -111,6 +257,7 @@ double lambda_max(const Csr& A, const std::vector<double>& d, int its)
   double lam = 1.0;
   for (int it = 0; it < its; ++it)
   {
+    halo_exchange(cm, L.plan, n, x);
     double nrm = 0.0;
     for (int i = 0; i < n; ++i)
     {
@@ -120,7 +267,7 @@ double lambda_max(const Csr& A, const std::vector<double>& d, int its)
       y[i] = t / d[i];
       nrm += y[i] * y[i];
     }
-    lam = std::sqrt(nrm);
+    lam = std::sqrt(allreduce_sum(cm, nrm));
     if (!(lam > 0.0))
       return 1.0;
     for (int i = 0; i < n; ++i)
@@ -129,11 +276,12 @@ double lambda_max(const Csr& A, const std::vector<double>& d, int its)
   return lam;
 }
 
-// Greedy aggregation on the free rows: pass 1 -- a node whose free neighbours are all unaggregated
-// founds an aggregate with them; pass 2 -- leftovers join a neighbouring aggregate (or found one).
-int aggregate(const Csr& A, const std::vector<char>& is_free, std::vector<int32_t>& agg)
+// Greedy aggregation on the rank-local graph of the free rows: pass 1 -- a node whose free
+// neighbours are all unaggregated founds an aggregate with them; pass 2 -- leftovers join a
+// neighbouring aggregate (or found one).  Ghost columns are ignored: aggregates never span ranks.
+int aggregate(const Csr& A, int n_owned, const std::vector<char>& is_free, std::vector<int32_t>& agg)
 {
-  const int n = A.n_rows;
+  const int n = n_owned;
   agg.assign((size_t)n, -1);
   int na = 0;
   for (int i = 0; i < n; ++i)
@@ -142,11 +290,14 @@ int aggregate(const Csr& A, const std::vector<char>& is_free, std::vector<int32_
       continue;
     bool ok = true;
     for (int32_t j = A.ptr[i]; j < A.ptr[i + 1] && ok; ++j)
-      ok = !is_free[A.cols[j]] || agg[A.cols[j]] < 0;
+    {
+      const int32_t c = A.cols[j];
+      ok = c >= n || !is_free[c] || agg[c] < 0;
+    }
     if (!ok)
       continue;
     for (int32_t j = A.ptr[i]; j < A.ptr[i + 1]; ++j)
-      if (is_free[A.cols[j]])
+      if (A.cols[j] < n && is_free[A.cols[j]])
         agg[A.cols[j]] = na;
     agg[i] = na++;
   }
@@ -155,7 +306,7 @@ int aggregate(const Csr& A, const std::vector<char>& is_free, std::vector<int32_
     if (!is_free[i] || agg[i] >= 0)
       continue;
     for (int32_t j = A.ptr[i]; j < A.ptr[i + 1] && agg[i] < 0; ++j)
-      if (agg[A.cols[j]] >= 0)
+      if (A.cols[j] < n && agg[A.cols[j]] >= 0)
         agg[i] = agg[A.cols[j]];
     if (agg[i] < 0)
       agg[i] = na++;
@@ -163,71 +314,232 @@ int aggregate(const Csr& A, const std::vector<char>& is_free, std::vector<int32_
   return na;
 }
 
-struct Level
+// Cholesky factorisation in place (lower triangle); false if the matrix is not positive definite
+bool cholesky(std::vector<double>& M, int n)
 {
-  Csr A, P; // P: this level -> next coarser one (empty on the coarsest level)
-  double lmax = 1.0;
-};
+  for (int j = 0; j < n; ++j)
+  {
+    double* rj = &M[(size_t)j * n];
+    double s = rj[j];
+    for (int k = 0; k < j; ++k)
+      s -= rj[k] * rj[k];
+    if (!(s > 0.0))
+      return false;
+    const double ljj = std::sqrt(s);
+    rj[j] = ljj;
+    for (int i = j + 1; i < n; ++i)
+    {
+      double* ri = &M[(size_t)i * n];
+      double t = ri[j];
+      for (int k = 0; k < j; ++k)
+        t -= ri[k] * rj[k];
+      ri[j] = t / ljj;
+    }
+  }
+  return true;
+}
+
+// gather the level on every rank, invert it, keep this rank's rows (columns in local layout)
+void finish_coarsest(Level& L, const Comm& cm)
+{
+  std::vector<long long> counts((size_t)cm.nranks, 0), off((size_t)cm.nranks + 1, 0);
+  long long mine = L.n_owned;
+  if (cm.nranks == 1)
+    counts[0] = mine;
+  else
+    cm.allgather(&mine, sizeof(mine), counts.data());
+  for (int r = 0; r < cm.nranks; ++r)
+    off[r + 1] = off[r] + counts[r];
+  const long long ng = off[cm.nranks];
+  L.n_global = ng;
+  L.dense = false;
+  if (ng == 0 || ng > DENSE_CAP)
+    return;
+  std::vector<char> blob;
+  put1<long long>(blob, L.A.nnz());
+  for (int i = 0; i < L.n_owned; ++i)
+    for (int32_t j = L.A.ptr[i]; j < L.A.ptr[i + 1]; ++j)
+    {
+      const int32_t c = L.A.cols[j];
+      const long long gc = c < L.n_owned ? off[cm.rank] + c : off[L.ghost_src[c - L.n_owned]] + L.ghost_rid[c - L.n_owned];
+      put1<long long>(blob, off[cm.rank] + i);
+      put1<long long>(blob, gc);
+      put1<double>(blob, L.A.vals[j]);
+    }
+  auto all = allgather_var(cm, blob);
+  const int n = (int)ng;
+  std::vector<double> M((size_t)n * n, 0.0);
+  for (auto& b : all)
+  {
+    Reader rd{b.data(), b.data() + b.size()};
+    const long long nz = rd.get1<long long>();
+    for (long long t = 0; t < nz; ++t)
+    {
+      const long long r = rd.get1<long long>(), c = rd.get1<long long>();
+      const double v = rd.get1<double>();
+      M[(size_t)r * n + c] += v;
+    }
+  }
+  // symmetrise against rounding differences between the ranks' copies of the same entry
+  for (int i = 0; i < n; ++i)
+    for (int j = i + 1; j < n; ++j)
+    {
+      const double v = 0.5 * (M[(size_t)i * n + j] + M[(size_t)j * n + i]);
+      M[(size_t)i * n + j] = M[(size_t)j * n + i] = v;
+    }
+  if (!cholesky(M, n))
+    return; // not SPD (should not happen): the caller smooths on this level instead
+  // rows [off[rank], off[rank] + n_owned) of M^-1: solve L L^T z = e_row
+  L.inv_rows.assign((size_t)L.n_owned * n, 0.0);
+  std::vector<int> perm((size_t)n); // local column -> global column
+  {
+    int p = 0;
+    for (long long g = off[cm.rank]; g < off[cm.rank + 1]; ++g)
+      perm[p++] = (int)g;
+    for (int r = 0; r < cm.nranks; ++r)
+      if (r != cm.rank)
+        for (long long g = off[r]; g < off[r + 1]; ++g)
+          perm[p++] = (int)g;
+  }
+  std::vector<double> z((size_t)n);
+#pragma omp parallel for firstprivate(z) schedule(static)
+  for (int row = 0; row < L.n_owned; ++row)
+  {
+    const int g = (int)off[cm.rank] + row;
+    std::fill(z.begin(), z.end(), 0.0);
+    for (int i = g; i < n; ++i) // forward: entries before g stay zero
+    {
+      double t = (i == g) ? 1.0 : 0.0;
+      const double* ri = &M[(size_t)i * n];
+      for (int k = g; k < i; ++k)
+        t -= ri[k] * z[k];
+      z[i] = t / ri[i];
+    }
+    for (int i = n - 1; i >= 0; --i) // backward with L^T
+    {
+      double t = z[i];
+      for (int k = i + 1; k < n; ++k)
+        t -= M[(size_t)k * n + i] * z[k];
+      z[i] = t / M[(size_t)i * n + i];
+    }
+    double* out = &L.inv_rows[(size_t)row * n];
+    for (int c = 0; c < n; ++c)
+      out[c] = z[perm[c]];
+  }
+  // all-gather plan: every rank sends all of its owned entries to every other rank
+  Plan& gp = L.gather_plan;
+  gp = Plan();
+  int slot = 0;
+  for (int r = 0; r < cm.nranks; ++r)
+  {
+    if (r == cm.rank)
+      continue;
+    gp.send_ranks.push_back(r);
+    for (int i = 0; i < L.n_owned; ++i)
+      gp.send_idx.push_back(i);
+    gp.send_offsets.push_back((int)gp.send_idx.size());
+    gp.recv_ranks.push_back(r);
+    for (long long t = 0; t < counts[r]; ++t)
+      gp.recv_idx.push_back(slot++);
+    gp.recv_offsets.push_back((int)gp.recv_idx.size());
+  }
+  L.dense = true;
+}
+
+void check_plan(const Plan& p, int n_owned, int n_ghost)
+{
+  PMGX_REQUIRE(p.send_offsets.size() == p.send_ranks.size() + 1 && p.recv_offsets.size() == p.recv_ranks.size() + 1,
+               "amg_setup: malformed halo plan");
+  PMGX_REQUIRE((size_t)p.send_offsets.back() == p.send_idx.size() && (size_t)p.recv_offsets.back() == p.recv_idx.size(),
+               "amg_setup: halo plan offsets do not match the index lists");
+  for (int32_t v : p.send_idx)
+    PMGX_REQUIRE(v >= 0 && v < n_owned, "amg_setup: send index out of range");
+  for (int32_t v : p.recv_idx)
+    PMGX_REQUIRE(v >= 0 && v < n_ghost, "amg_setup: ghost slot out of range");
+}
 } // namespace
 
-struct pmgx_amg_hier
+void setup(Hierarchy& H, Csr A0, int n_owned, int n_ghost, const Plan& plan0, const Comm& cm, int min_coarse,
+           int max_levels)
 {
-  std::vector<Level> levels;
-};
+  H.levels.clear();
+  check_plan(plan0, n_owned, n_ghost);
+  Level L;
+  L.A = std::move(A0);
+  L.A.n_rows = n_owned;
+  L.A.n_cols = n_owned + n_ghost;
+  L.n_owned = n_owned;
+  L.n_ghost = n_ghost;
+  L.plan = plan0;
+  for (int32_t c : L.A.cols)
+    PMGX_REQUIRE(c >= 0 && c < n_owned + n_ghost, "amg_setup: column out of range");
+  // who owns my ghosts, and under which index: every rank tells its neighbours its send lists
+  L.ghost_src.assign((size_t)n_ghost, -1);
+  L.ghost_rid.assign((size_t)n_ghost, -1);
+  if (cm.nranks > 1)
+  {
+    std::vector<std::vector<char>> msgs(plan0.send_ranks.size());
+    for (size_t k = 0; k < plan0.send_ranks.size(); ++k)
+      put(msgs[k], plan0.send_idx.data() + plan0.send_offsets[k], (size_t)(plan0.send_offsets[k + 1] - plan0.send_offsets[k]));
+    for (auto& m : neighbor_exchange(cm, plan0.send_ranks, msgs))
+    {
+      const auto it = std::find(plan0.recv_ranks.begin(), plan0.recv_ranks.end(), m.first);
+      PMGX_REQUIRE(it != plan0.recv_ranks.end(), "amg_setup: rank %d sends to rank %d, which does not expect it", m.first,
+                   cm.rank);
+      const size_t k = it - plan0.recv_ranks.begin();
+      const size_t cnt = (size_t)(plan0.recv_offsets[k + 1] - plan0.recv_offsets[k]);
+      PMGX_REQUIRE(m.second.size() == cnt * sizeof(int32_t), "amg_setup: send / receive counts of ranks %d -> %d differ",
+                   m.first, cm.rank);
+      Reader rd{m.second.data(), m.second.data() + m.second.size()};
+      for (size_t t = 0; t < cnt; ++t)
+      {
+        const int32_t slot = plan0.recv_idx[plan0.recv_offsets[k] + t];
+        L.ghost_src[slot] = m.first;
+        L.ghost_rid[slot] = rd.get1<int32_t>();
+      }
+    }
+  }
 
-extern "C"
-{
-int pmgx_amg_setup_h(int n_rows, const int32_t* row_ptr_h, const int32_t* cols_h, const double* values_h,
-                     int min_coarse, int max_levels, pmgx_amg_hier** out)
-{
-  PMGX_API_BEGIN
-  PMGX_REQUIRE(out && row_ptr_h && n_rows >= 0 && max_levels >= 1, "amg_setup: bad arguments");
-  std::unique_ptr<pmgx_amg_hier> H(new pmgx_amg_hier());
-  Csr A;
-  A.n_rows = A.n_cols = n_rows;
-  A.ptr.assign(row_ptr_h, row_ptr_h + n_rows + 1);
-  const long long nnz = row_ptr_h[n_rows];
-  PMGX_REQUIRE(nnz == 0 || (cols_h && values_h), "amg_setup: null matrix arrays");
-  A.cols.assign(cols_h, cols_h + nnz);
-  A.vals.assign(values_h, values_h + nnz);
-  for (int32_t c : A.cols)
-    PMGX_REQUIRE(c >= 0 && c < n_rows, "amg_setup: column out of range (single-rank matrices only)");
   while (true)
   {
-    Level L;
-    L.A = std::move(A);
     const Csr& M = L.A;
+    const int n = L.n_owned;
     const std::vector<double> d = diagonal(M);
     for (double v : d)
       PMGX_REQUIRE(v > 0.0, "amg_setup: non-positive diagonal entry");
-    L.lmax = 1.1 * lambda_max(M, d, 15);
+    L.lmax = 1.1 * lambda_max(L, d, cm, 15);
     // free rows: everything except rows holding only their diagonal (Dirichlet rows, src/csr.hpp:84-86)
-    std::vector<char> is_free((size_t)M.n_rows, 0);
-    int n_free = 0;
-    for (int i = 0; i < M.n_rows; ++i)
+    std::vector<char> is_free((size_t)n, 0);
+    long long n_free = 0;
+    for (int i = 0; i < n; ++i)
     {
       is_free[i] = (M.ptr[i + 1] - M.ptr[i]) > 1;
       n_free += is_free[i];
     }
-    const bool last = n_free <= min_coarse || (int)H->levels.size() + 1 >= max_levels;
+    const long long n_free_g = allreduce_sum(cm, n_free);
+    bool last = n_free_g <= min_coarse || (int)H.levels.size() + 1 >= max_levels;
+    std::vector<int32_t> agg;
+    int na = 0;
+    if (!last)
+    {
+      na = aggregate(M, n, is_free, agg);
+      const long long na_g = allreduce_sum(cm, (long long)na);
+      last = na_g == 0 || na_g >= n_free_g;
+    }
     if (last)
     {
-      H->levels.push_back(std::move(L));
+      finish_coarsest(L, cm);
+      H.levels.push_back(std::move(L));
       break;
     }
-    std::vector<int32_t> agg;
-    const int na = aggregate(M, is_free, agg);
-    if (na == 0 || na >= n_free)
-    {
-      H->levels.push_back(std::move(L));
-      break;
-    }
-    // tentative prolongator T, then P = T - omega D^-1 (A T)
-    Csr T;
-    T.n_rows = M.n_rows;
-    T.n_cols = na;
-    T.ptr.assign((size_t)M.n_rows + 1, 0);
-    for (int i = 0; i < M.n_rows; ++i)
+    // tentative prolongator T and the rank-local filtered matrix A_loc (ghost couplings lumped onto
+    // the diagonal: A_loc 1 = A 1, so P still reproduces constants next to a partition interface)
+    Csr T, Aloc;
+    T.n_rows = n, T.n_cols = na;
+    T.ptr.assign((size_t)n + 1, 0);
+    Aloc.n_rows = n, Aloc.n_cols = n;
+    Aloc.ptr.assign((size_t)n + 1, 0);
+    for (int i = 0; i < n; ++i)
     {
       if (agg[i] >= 0)
       {
@@ -235,14 +547,31 @@ int pmgx_amg_setup_h(int n_rows, const int32_t* row_ptr_h, const int32_t* cols_h
         T.vals.push_back(1.0);
       }
       T.ptr[i + 1] = (int32_t)T.cols.size();
+      double lump = 0.0;
+      size_t dpos = (size_t)-1;
+      for (int32_t j = M.ptr[i]; j < M.ptr[i + 1]; ++j)
+      {
+        if (M.cols[j] >= n)
+        {
+          lump += M.vals[j];
+          continue;
+        }
+        if (M.cols[j] == i)
+          dpos = Aloc.cols.size();
+        Aloc.cols.push_back(M.cols[j]);
+        Aloc.vals.push_back(M.vals[j]);
+      }
+      if (dpos != (size_t)-1)
+        Aloc.vals[dpos] += lump;
+      Aloc.ptr[i + 1] = (int32_t)Aloc.cols.size();
     }
-    Csr AT = spgemm(M, T);
+    Csr AT = spgemm(Aloc, T);
     const double omega = 4.0 / (3.0 * L.lmax);
     Csr P;
-    P.n_rows = M.n_rows;
+    P.n_rows = n;
     P.n_cols = na;
-    P.ptr.assign((size_t)M.n_rows + 1, 0);
-    for (int i = 0; i < M.n_rows; ++i)
+    P.ptr.assign((size_t)n + 1, 0);
+    for (int i = 0; i < n; ++i)
     {
       // merge row i of T (at most one entry) with -omega/d_i * row i of AT (sorted)
       const int32_t tc = agg[i];
@@ -272,23 +601,229 @@ int pmgx_amg_setup_h(int n_rows, const int32_t* row_ptr_h, const int32_t* cols_h
       }
       P.ptr[i + 1] = (int32_t)P.cols.size();
     }
-    Csr AP = spgemm(M, P);
-    A = spgemm(transpose(P), AP); // Galerkin product
+    // prolongator rows of my ghosts: the owners send the rows of the dofs on their send lists
+    struct GhostRow
+    {
+      std::vector<int32_t> cols; // owner-local aggregate ids
+      std::vector<double> vals;
+    };
+    std::vector<GhostRow> grow((size_t)L.n_ghost);
+    if (cm.nranks > 1)
+    {
+      std::vector<std::vector<char>> msgs(L.plan.send_ranks.size());
+      for (size_t k = 0; k < L.plan.send_ranks.size(); ++k)
+        for (int t = L.plan.send_offsets[k]; t < L.plan.send_offsets[k + 1]; ++t)
+        {
+          const int32_t i = L.plan.send_idx[t];
+          const int32_t len = P.ptr[i + 1] - P.ptr[i];
+          put1<int32_t>(msgs[k], len);
+          put(msgs[k], P.cols.data() + P.ptr[i], (size_t)len);
+          put(msgs[k], P.vals.data() + P.ptr[i], (size_t)len);
+        }
+      for (auto& m : neighbor_exchange(cm, L.plan.send_ranks, msgs))
+      {
+        const auto it = std::find(L.plan.recv_ranks.begin(), L.plan.recv_ranks.end(), m.first);
+        if (it == L.plan.recv_ranks.end())
+          continue;
+        const size_t k = it - L.plan.recv_ranks.begin();
+        Reader rd{m.second.data(), m.second.data() + m.second.size()};
+        for (int t = L.plan.recv_offsets[k]; t < L.plan.recv_offsets[k + 1]; ++t)
+        {
+          GhostRow& g = grow[L.plan.recv_idx[t]];
+          const int32_t len = rd.get1<int32_t>();
+          g.cols.resize((size_t)len);
+          g.vals.resize((size_t)len);
+          rd.get(g.cols.data(), (size_t)len);
+          rd.get(g.vals.data(), (size_t)len);
+        }
+      }
+    }
+    // provisional ghost aggregates, numbered in (owner, owner-local id) order
+    std::map<std::pair<int, int32_t>, int32_t> gmap;
+    for (int g = 0; g < L.n_ghost; ++g)
+      for (int32_t c : grow[g].cols)
+        gmap[{L.ghost_src[g], c}] = 0;
+    {
+      int32_t id = 0;
+      for (auto& kv : gmap)
+        kv.second = id++;
+    }
+    const int n_prov = (int)gmap.size();
+    Csr Pext;
+    Pext.n_rows = n + L.n_ghost;
+    Pext.n_cols = na + n_prov;
+    Pext.ptr = P.ptr;
+    Pext.cols = P.cols;
+    Pext.vals = P.vals;
+    Pext.ptr.resize((size_t)n + L.n_ghost + 1);
+    for (int g = 0; g < L.n_ghost; ++g)
+    {
+      std::vector<std::pair<int32_t, double>> row;
+      for (size_t t = 0; t < grow[g].cols.size(); ++t)
+        row.emplace_back(na + gmap[{L.ghost_src[g], grow[g].cols[t]}], grow[g].vals[t]);
+      std::sort(row.begin(), row.end());
+      for (auto& e : row)
+      {
+        Pext.cols.push_back(e.first);
+        Pext.vals.push_back(e.second);
+      }
+      Pext.ptr[(size_t)n + g + 1] = (int32_t)Pext.cols.size();
+    }
+    Csr AP = spgemm(M, Pext);
+    Csr Ac = spgemm(transpose(P), AP); // Galerkin product: owned coarse rows, owned + ghost coarse columns
+    // keep only the ghost aggregates A_c references; the (owner, id) order survives, so the column
+    // renumbering is monotone and the rows stay sorted
+    std::vector<int32_t> remap((size_t)n_prov, -1);
+    for (int32_t c : Ac.cols)
+      if (c >= na)
+        remap[c - na] = 0;
+    Level C;
+    C.n_owned = na;
+    {
+      int32_t id = 0;
+      for (auto& kv : gmap)
+        if (remap[kv.second] == 0)
+        {
+          remap[kv.second] = id++;
+          C.ghost_src.push_back(kv.first.first);
+          C.ghost_rid.push_back(kv.first.second);
+        }
+      C.n_ghost = id;
+    }
+    for (int32_t& c : Ac.cols)
+      if (c >= na)
+        c = na + remap[c - na];
+    Ac.n_cols = na + C.n_ghost;
+    C.A = std::move(Ac);
+    // coarse halo plan: my ghosts are grouped by owner already; tell the owners what I need
+    {
+      Plan& cp = C.plan;
+      std::vector<int> req_ranks;
+      std::vector<std::vector<char>> req;
+      for (int g = 0; g < C.n_ghost; ++g)
+      {
+        if (req_ranks.empty() || req_ranks.back() != C.ghost_src[g])
+        {
+          req_ranks.push_back(C.ghost_src[g]);
+          req.emplace_back();
+        }
+        put1<int32_t>(req.back(), C.ghost_rid[g]);
+      }
+      std::map<int, std::vector<int32_t>> wanted; // requester -> my aggregate ids
+      if (cm.nranks > 1)
+        for (auto& m : neighbor_exchange(cm, req_ranks, req))
+        {
+          std::vector<int32_t> ids(m.second.size() / sizeof(int32_t));
+          if (!ids.empty())
+            std::memcpy(ids.data(), m.second.data(), ids.size() * sizeof(int32_t));
+          wanted[m.first] = std::move(ids);
+        }
+      // symmetric neighbourhoods (the peer-memory halo pairs every send with a receive): a rank I
+      // only send to / only receive from gets an empty segment in the other direction
+      std::map<int, std::vector<int32_t>> needed; // owner -> ghost slots
+      for (int g = 0; g < C.n_ghost; ++g)
+        needed[C.ghost_src[g]].push_back(g);
+      std::vector<int> nbrs;
+      for (auto& kv : wanted)
+        nbrs.push_back(kv.first);
+      for (auto& kv : needed)
+        nbrs.push_back(kv.first);
+      std::sort(nbrs.begin(), nbrs.end());
+      nbrs.erase(std::unique(nbrs.begin(), nbrs.end()), nbrs.end());
+      for (int r : nbrs)
+      {
+        cp.send_ranks.push_back(r);
+        for (int32_t id : wanted[r])
+        {
+          PMGX_REQUIRE(id >= 0 && id < na, "amg_setup: rank %d asks for aggregate %d of %d", r, id, na);
+          cp.send_idx.push_back(id);
+        }
+        cp.send_offsets.push_back((int)cp.send_idx.size());
+        cp.recv_ranks.push_back(r);
+        for (int32_t g : needed[r])
+          cp.recv_idx.push_back(g);
+        cp.recv_offsets.push_back((int)cp.recv_idx.size());
+      }
+    }
     L.P = std::move(P);
-    H->levels.push_back(std::move(L));
+    H.levels.push_back(std::move(L));
+    L = std::move(C);
   }
+}
+} // namespace amg
+} // namespace pmgx
+
+struct pmgx_amg_hier
+{
+  pmgx::amg::Hierarchy H;
+};
+
+using pmgx::amg::Level;
+
+extern "C"
+{
+int pmgx_amg_setup_dist_h(int rank, int nranks, int n_owned, int n_ghost, const int32_t* row_ptr_h,
+                          const int32_t* cols_h, const double* values_h, int n_send_nbr, const int* send_ranks_h,
+                          const int* send_offsets_h, const int32_t* send_idx_h, int n_recv_nbr,
+                          const int* recv_ranks_h, const int* recv_offsets_h, const int32_t* recv_idx_h,
+                          pmgx_allgather_fn allgather, void* user, int min_coarse, int max_levels,
+                          pmgx_amg_hier** out)
+{
+  PMGX_API_BEGIN
+  PMGX_REQUIRE(out && row_ptr_h && n_owned >= 0 && n_ghost >= 0 && max_levels >= 1, "amg_setup: bad arguments");
+  PMGX_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "amg_setup: bad rank");
+  PMGX_REQUIRE(nranks == 1 || allgather, "amg_setup: an all-gather callback is needed on more than one rank");
+  std::unique_ptr<pmgx_amg_hier> H(new pmgx_amg_hier());
+  pmgx::amg::Csr A;
+  A.ptr.assign(row_ptr_h, row_ptr_h + n_owned + 1);
+  const long long nnz = row_ptr_h[n_owned];
+  PMGX_REQUIRE(nnz == 0 || (cols_h && values_h), "amg_setup: null matrix arrays");
+  A.cols.assign(cols_h, cols_h + nnz);
+  A.vals.assign(values_h, values_h + nnz);
+  // rows sorted by column (owned block first): the set-up relies on it
+  for (int i = 0; i < n_owned; ++i)
+    for (int32_t j = A.ptr[i] + 1; j < A.ptr[i + 1]; ++j)
+      PMGX_REQUIRE(A.cols[j - 1] < A.cols[j], "amg_setup: row %d is not sorted by column", i);
+  pmgx::amg::Plan pl;
+  if (n_send_nbr > 0)
+  {
+    pl.send_ranks.assign(send_ranks_h, send_ranks_h + n_send_nbr);
+    pl.send_offsets.assign(send_offsets_h, send_offsets_h + n_send_nbr + 1);
+    pl.send_idx.assign(send_idx_h, send_idx_h + send_offsets_h[n_send_nbr]);
+  }
+  if (n_recv_nbr > 0)
+  {
+    pl.recv_ranks.assign(recv_ranks_h, recv_ranks_h + n_recv_nbr);
+    pl.recv_offsets.assign(recv_offsets_h, recv_offsets_h + n_recv_nbr + 1);
+    pl.recv_idx.assign(recv_idx_h, recv_idx_h + recv_offsets_h[n_recv_nbr]);
+  }
+  pmgx::amg::Comm cm;
+  cm.rank = rank;
+  cm.nranks = nranks;
+  cm.allgather = [allgather, user](const void* mine, size_t bytes, void* all)
+  {
+    if (allgather(user, mine, bytes, all) != 0)
+      throw std::runtime_error("amg set-up: the all-gather callback failed");
+  };
+  pmgx::amg::setup(H->H, std::move(A), n_owned, n_ghost, pl, cm, min_coarse, max_levels);
   *out = H.release();
   PMGX_API_END
 }
 
-int pmgx_amg_num_levels(pmgx_amg_hier* h) { return h ? (int)h->levels.size() : -1; }
+int pmgx_amg_setup_h(int n_rows, const int32_t* row_ptr_h, const int32_t* cols_h, const double* values_h,
+                     int min_coarse, int max_levels, pmgx_amg_hier** out)
+{
+  return pmgx_amg_setup_dist_h(0, 1, n_rows, 0, row_ptr_h, cols_h, values_h, 0, nullptr, nullptr, nullptr, 0, nullptr,
+                               nullptr, nullptr, nullptr, nullptr, min_coarse, max_levels, out);
+}
 
-/* out_h[0] = rows of A, [1] = nnz(A), [2] = columns of P (0 on the coarsest level), [3] = nnz(P) */
+int pmgx_amg_num_levels(pmgx_amg_hier* h) { return h ? (int)h->H.levels.size() : -1; }
+
 int pmgx_amg_level_sizes(pmgx_amg_hier* h, int level, long long* out_h)
 {
   PMGX_API_BEGIN
-  PMGX_REQUIRE(h && out_h && level >= 0 && level < (int)h->levels.size(), "amg_level_sizes: bad arguments");
-  const Level& L = h->levels[level];
+  PMGX_REQUIRE(h && out_h && level >= 0 && level < (int)h->H.levels.size(), "amg_level_sizes: bad arguments");
+  const Level& L = h->H.levels[level];
   out_h[0] = L.A.n_rows;
   out_h[1] = L.A.nnz();
   out_h[2] = L.P.n_cols;
@@ -300,8 +835,8 @@ int pmgx_amg_level_get(pmgx_amg_hier* h, int level, int32_t* a_ptr_h, int32_t* a
                        int32_t* p_ptr_h, int32_t* p_cols_h, double* p_vals_h, double* lmax_h)
 {
   PMGX_API_BEGIN
-  PMGX_REQUIRE(h && level >= 0 && level < (int)h->levels.size(), "amg_level_get: bad arguments");
-  const Level& L = h->levels[level];
+  PMGX_REQUIRE(h && level >= 0 && level < (int)h->H.levels.size(), "amg_level_get: bad arguments");
+  const Level& L = h->H.levels[level];
   if (a_ptr_h)
     std::copy(L.A.ptr.begin(), L.A.ptr.end(), a_ptr_h);
   if (a_cols_h)
@@ -316,6 +851,50 @@ int pmgx_amg_level_get(pmgx_amg_hier* h, int level, int32_t* a_ptr_h, int32_t* a
     std::copy(L.P.vals.begin(), L.P.vals.end(), p_vals_h);
   if (lmax_h)
     *lmax_h = L.lmax;
+  PMGX_API_END
+}
+
+int pmgx_amg_level_dist_sizes(pmgx_amg_hier* h, int level, long long* out_h)
+{
+  PMGX_API_BEGIN
+  PMGX_REQUIRE(h && out_h && level >= 0 && level < (int)h->H.levels.size(), "amg_level_dist_sizes: bad arguments");
+  const Level& L = h->H.levels[level];
+  out_h[0] = L.n_owned;
+  out_h[1] = L.n_ghost;
+  out_h[2] = (long long)L.plan.send_ranks.size();
+  out_h[3] = (long long)L.plan.send_idx.size();
+  out_h[4] = (long long)L.plan.recv_ranks.size();
+  out_h[5] = (long long)L.plan.recv_idx.size();
+  out_h[6] = L.dense ? 1 : 0;
+  out_h[7] = L.n_global;
+  PMGX_API_END
+}
+
+int pmgx_amg_level_dist_get(pmgx_amg_hier* h, int level, int* ghost_src_h, int32_t* ghost_rid_h, int* send_ranks_h,
+                            int* send_offsets_h, int32_t* send_idx_h, int* recv_ranks_h, int* recv_offsets_h,
+                            int32_t* recv_idx_h, double* inv_rows_h)
+{
+  PMGX_API_BEGIN
+  PMGX_REQUIRE(h && level >= 0 && level < (int)h->H.levels.size(), "amg_level_dist_get: bad arguments");
+  const Level& L = h->H.levels[level];
+  if (ghost_src_h)
+    std::copy(L.ghost_src.begin(), L.ghost_src.end(), ghost_src_h);
+  if (ghost_rid_h)
+    std::copy(L.ghost_rid.begin(), L.ghost_rid.end(), ghost_rid_h);
+  if (send_ranks_h)
+    std::copy(L.plan.send_ranks.begin(), L.plan.send_ranks.end(), send_ranks_h);
+  if (send_offsets_h)
+    std::copy(L.plan.send_offsets.begin(), L.plan.send_offsets.end(), send_offsets_h);
+  if (send_idx_h)
+    std::copy(L.plan.send_idx.begin(), L.plan.send_idx.end(), send_idx_h);
+  if (recv_ranks_h)
+    std::copy(L.plan.recv_ranks.begin(), L.plan.recv_ranks.end(), recv_ranks_h);
+  if (recv_offsets_h)
+    std::copy(L.plan.recv_offsets.begin(), L.plan.recv_offsets.end(), recv_offsets_h);
+  if (recv_idx_h)
+    std::copy(L.plan.recv_idx.begin(), L.plan.recv_idx.end(), recv_idx_h);
+  if (inv_rows_h)
+    std::copy(L.inv_rows.begin(), L.inv_rows.end(), inv_rows_h);
   PMGX_API_END
 }
 

@@ -6,6 +6,7 @@
 #include "common.hpp"
 #include "operator.hpp"
 #include "csr.hpp"
+#include "solvers.hpp"
 
 namespace pmgx
 {
@@ -106,6 +107,56 @@ __global__ void k_extract_diag_inv(int n_rows, const double* __restrict__ vals,
       d = 1.0 / vals[j]; // src/csr.hpp:104-111
   dinv[i] = d;
 }
+
+// rectangular product for the AMG transfer operators: same kernel body with LANES lanes per row
+template <int LANES, bool ACCUM>
+__global__ void __launch_bounds__(ST)
+k_spmv_rect(int n_rows, const double* __restrict__ vals, const int32_t* __restrict__ ptr,
+            const int32_t* __restrict__ cols, const double* __restrict__ x, double* __restrict__ y)
+{
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = gt / LANES, lane = gt % LANES;
+  double s = 0.0;
+  if (row < n_rows)
+  {
+    const int e = ptr[row + 1];
+    for (int j = ptr[row] + lane; j < e; j += LANES)
+      s = fma(vals[j], x[cols[j]], s);
+  }
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1)
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (row < n_rows && lane == 0)
+    y[row] = ACCUM ? y[row] + s : s;
+}
+} // namespace
+
+void spmv_rect(pmgx_ctx* c, int n_rows, const int32_t* row_ptr, const int32_t* cols, const double* vals,
+               const double* x, double* y, bool accumulate, int lanes)
+{
+  if (n_rows <= 0)
+    return;
+  const int grid = (int)(((long long)n_rows * lanes + ST - 1) / ST);
+  if (lanes == 32)
+  {
+    if (accumulate)
+      k_spmv_rect<32, true><<<grid, ST, 0, c->stream>>>(n_rows, vals, row_ptr, cols, x, y);
+    else
+      k_spmv_rect<32, false><<<grid, ST, 0, c->stream>>>(n_rows, vals, row_ptr, cols, x, y);
+  }
+  else
+  {
+    if (accumulate)
+      k_spmv_rect<8, true><<<grid, ST, 0, c->stream>>>(n_rows, vals, row_ptr, cols, x, y);
+    else
+      k_spmv_rect<8, false><<<grid, ST, 0, c->stream>>>(n_rows, vals, row_ptr, cols, x, y);
+  }
+  check_launch("k_spmv_rect");
+  count_launch(c);
+}
+
+namespace
+{
 } // namespace
 
 void CsrOperator::apply(double* x, double* y)

@@ -117,22 +117,29 @@ static void halo_fwd_begin_p2p(pmgx_halo* h, double* x, const double* sub)
 {
   pmgx_ctx* c = h->ctx;
   const int ns = h->n_send(), nr = h->n_recv();
-  if (ns > 0)
+  // a neighbour with an EMPTY segment still takes part in the flag handshake (the coarse levels of
+  // the AMG hierarchy pair every send with a receive, amg_setup.cpp): the pack kernel runs whenever
+  // there is a destination, the wait whenever there is a source
+  if (!h->send_ranks.empty())
   {
-    k_pack_p2p<<<(ns + PT - 1) / PT, PT, 0, c->comm_stream>>>(ns, (int)h->send_ranks.size(), h->d_send_offsets.p,
+    k_pack_p2p<<<std::max((ns + PT - 1) / PT, 1), PT, 0, c->comm_stream>>>(ns, (int)h->send_ranks.size(), h->d_send_offsets.p,
                                                              h->send_idx.p, x, sub, h->d_peer_dst.p, h->d_peer_stride.p,
                                                              h->d_peer_flag.p, h->d_epoch.p, h->d_ticket.p);
     check_launch("k_pack_p2p");
     count_launch(c);
   }
-  if (nr > 0)
+  if (!h->recv_ranks.empty())
   {
     const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(h->xbuf + 2 * (size_t)std::max(nr, 1));
     k_wait_p2p<<<1, 32, 0, c->comm_stream>>>((int)h->recv_ranks.size(), flags, h->d_epoch.p,
                                              c->p2p_timeout_ns);
-    k_unpack_cg<<<(nr + PT - 1) / PT, PT, 0, c->comm_stream>>>(nr, h->recv_idx.p, h->xbuf, h->d_epoch.p, x + h->n_owned);
+    count_launch(c);
+    if (nr > 0)
+    {
+      k_unpack_cg<<<(nr + PT - 1) / PT, PT, 0, c->comm_stream>>>(nr, h->recv_idx.p, h->xbuf, h->d_epoch.p, x + h->n_owned);
+      count_launch(c);
+    }
     check_launch("k_unpack(p2p)");
-    count_launch(c, 2);
   }
 }
 
@@ -140,8 +147,10 @@ void halo_fwd_begin(pmgx_halo* h, double* x, const double* sub)
 {
   pmgx_ctx* c = h->ctx;
   const int ns = h->n_send(), nr = h->n_recv();
-  if (ns == 0 && nr == 0)
+  if (h->send_ranks.empty() && h->recv_ranks.empty())
     return;
+  if (!h->p2p && ns == 0 && nr == 0)
+    return; // NCCL path: empty segments are skipped on both sides
   PMGX_CUDA(cudaEventRecord(h->ev_ready, c->stream));
   PMGX_CUDA(cudaStreamWaitEvent(c->comm_stream, h->ev_ready, 0));
   if (h->p2p)
@@ -162,11 +171,13 @@ void halo_fwd_begin(pmgx_halo* h, double* x, const double* sub)
   PMGX_REQUIRE(c->comm != nullptr, "halo exchange needs a multi-rank context");
   PMGX_NCCL(ncclGroupStart());
   for (size_t i = 0; i < h->recv_ranks.size(); ++i)
-    PMGX_NCCL(ncclRecv(h->recv_buf.p + h->recv_offsets[i], h->recv_offsets[i + 1] - h->recv_offsets[i],
-                       ncclDouble, h->recv_ranks[i], c->comm, c->comm_stream));
+    if (h->recv_offsets[i + 1] > h->recv_offsets[i])
+      PMGX_NCCL(ncclRecv(h->recv_buf.p + h->recv_offsets[i], h->recv_offsets[i + 1] - h->recv_offsets[i],
+                         ncclDouble, h->recv_ranks[i], c->comm, c->comm_stream));
   for (size_t i = 0; i < h->send_ranks.size(); ++i)
-    PMGX_NCCL(ncclSend(h->send_buf.p + h->send_offsets[i], h->send_offsets[i + 1] - h->send_offsets[i],
-                       ncclDouble, h->send_ranks[i], c->comm, c->comm_stream));
+    if (h->send_offsets[i + 1] > h->send_offsets[i])
+      PMGX_NCCL(ncclSend(h->send_buf.p + h->send_offsets[i], h->send_offsets[i + 1] - h->send_offsets[i],
+                         ncclDouble, h->send_ranks[i], c->comm, c->comm_stream));
   PMGX_NCCL(ncclGroupEnd());
   if (nr > 0)
   {

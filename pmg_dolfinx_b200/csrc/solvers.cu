@@ -9,6 +9,7 @@
 #include "common.hpp"
 #include "operator.hpp"
 #include "reduce.cuh"
+#include "solvers.hpp"
 
 #include <cmath>
 #include <cstdlib>
@@ -188,7 +189,8 @@ k_cgcg_init(const double* __restrict__ b, const double* __restrict__ q, const do
   {
     const double rv = q ? q[i] * (-1.0) + b[i] : b[i];
     r[i] = rv;
-    u[i] = rv * dinv[i];
+    if (dinv) // null: u = M^-1 r comes from the multilevel preconditioner right after this pass
+      u[i] = rv * dinv[i];
     if (zero_x)
       x[i] = 0.0;
   }
@@ -220,7 +222,8 @@ k_cgcg_update(const double* __restrict__ sc_cur, const double* __restrict__ sc_o
     x[i] = fma(alpha, pv, x[i]);
     const double rv = fma(-alpha, sv, r[i]);
     r[i] = rv;
-    u[i] = rv * dinv[i];
+    if (dinv)
+      u[i] = rv * dinv[i];
   }
   if (blockIdx.x == 0 && threadIdx.x == 0)
   {
@@ -251,33 +254,12 @@ void check(const char* w) { check_launch(w); }
 } // namespace
 } // namespace pmgx
 
-// ------------------------------------------------------------------------- Chebyshev --
-struct pmgx_cheb
-{
-  pmgx_ctx* ctx = nullptr;
-  int n_owned = 0, n_ghost = 0;
-  double eig_min = 0.0, eig_max = 1.0;
-  int max_iter = 0;
-  pmgx::DevBuf<double> z, q, r; // work vectors (owned + ghost), src/chebyshev.hpp:101-105
-};
 
 namespace pmgx
 {
-// x <- Chebyshev(A, x, b). hist: max_iter+1 residual norms or nullptr.
-// final_r says what the caller needs of the recurrence residual r = b - A x_final afterwards:
-//   CHEB_R_NONE   nothing: the last iteration of the reference (one apply + one pass that only
-//                 feed r and a z nobody reads, chebyshev.hpp:76-83) is dropped; x is bit-identical
-//   CHEB_R_FULL   s->r holds r
-//   CHEB_R_SPLIT  s->r - s->q is r (the caller folds the subtraction into its own gather)
-enum ChebResidual
-{
-  CHEB_R_NONE = 0,
-  CHEB_R_FULL = 1,
-  CHEB_R_SPLIT = 2
-};
 
-void cheb_solve(pmgx_cheb* s, pmgx_operator* A, double* x, const double* b, double* hist,
-                bool x_is_zero = false, ChebResidual final_r = CHEB_R_FULL)
+void cheb_solve(pmgx_cheb* s, pmgx_operator* A, double* x, const double* b, double* hist, bool x_is_zero,
+                ChebResidual final_r)
 {
   pmgx_ctx* c = s->ctx;
   const long long n = s->n_owned;
@@ -361,26 +343,6 @@ void cheb_solve(pmgx_cheb* s, pmgx_operator* A, double* x, const double* b, doub
 } // namespace pmgx
 
 // -------------------------------------------------------------------------------- CG --
-struct pmgx_cg
-{
-  pmgx_ctx* ctx = nullptr;
-  int n_owned = 0, n_ghost = 0;
-  int max_iter = 0;
-  double rtol = 0.0;
-  bool store = false;
-  pmgx::DevBuf<double> r, y, p; // src/cg.hpp:241-244
-  pmgx::DevBuf<double> slab;    // r, w, p, u, s of the single-reduction coarse variant, contiguous (lazy)
-  // CUDA graph of one block of `graph_len` coarse iterations (captured from the stream on first use,
-  // replayed between the host's convergence checks): the ~8 small launches and 4 cross-stream
-  // events of an iteration cost more in launch gaps than the kernels of a 1.6 M-dof level run
-  cudaGraphExec_t graph = nullptr;
-  const void* graph_key[3] = {nullptr, nullptr, nullptr}; // operator, x, block length
-  int graph_launches = 0;
-  bool graph_off = false;
-  std::vector<double> alphas, betas, residuals; // stored coefficients (:213-218)
-  std::vector<double> history;                  // every iteration's r.M^-1 r
-  double rnorm0 = 0.0;
-};
 
 namespace pmgx
 {
@@ -435,16 +397,20 @@ int cg_solve(pmgx_cg* s, pmgx_operator* A, double* x, const double* b)
 
 namespace pmgx
 {
-// Coarse-level PCG (Jacobi), single-reduction form: mathematically the CG of src/cg.hpp, but the
-// two inner products of an iteration are formed together in one pass, alpha/beta never leave
-// the device and the host only looks at r.D^-1 r every `check_every` iterations.  Iteration
-// counts of this inner solve are not a parity quantity (the reference runs PETSc CG + BoomerAMG
-// here, src/amg.hpp:33-47).  s->y doubles as w = A u; work vectors p, s2, u are the solver's.
-int cgcg_solve(pmgx_cg* s, pmgx_operator* A, double* x, const double* b, int check_every, bool x_is_zero)
+// Coarse-level PCG, single-reduction form: mathematically the CG of src/cg.hpp, but the two inner
+// products of an iteration are formed together in one pass, alpha/beta never leave the device
+// and the host only looks at r.M^-1 r every `check_every` iterations.  M is the smoothed-
+// aggregation V-cycle of amg.cu (the reference runs PETSc CG + BoomerAMG here, src/amg.hpp:33-47)
+// or Jacobi.  Iteration counts of this inner solve are not a parity quantity.
+int cgcg_solve(pmgx_coarse* co, double* x, const double* b, bool x_is_zero)
 {
+  pmgx_cg* s = co->cg;
+  pmgx_operator* A = co->A;
+  Precond* M = co->M;
+  const int check_every = co->check_every;
   pmgx_ctx* c = s->ctx;
   const long long n = s->n_owned;
-  const double* dinv = A->diag_inv.p;
+  const double* dinv = M ? nullptr : A->diag_inv.p;
   const int grid = fused_grid(c, n);
   const size_t nt = (size_t)s->n_owned + s->n_ghost;
   // the five work vectors live in one slab
@@ -485,6 +451,8 @@ int cgcg_solve(pmgx_cg* s, pmgx_operator* A, double* x, const double* b, int che
   k_cgcg_init<<<grid, FT, 0, c->stream>>>(b, x_is_zero ? nullptr : w, dinv, cr, cu, x, x_is_zero, n);
   check("k_cgcg_init");
   count_launch(c);
+  if (M)
+    M->apply(cr, cu);
   spmv_dots(sc, 16);
   s->history.clear();
   const double rtol2 = s->rtol * s->rtol;
@@ -499,7 +467,11 @@ int cgcg_solve(pmgx_cg* s, pmgx_operator* A, double* x, const double* b, int che
     check("k_cgcg_update");
     count_launch(c);
     if (k + 1 < s->max_iter)
+    {
+      if (M)
+        M->apply(cr, cu);
       spmv_dots(sc + 2 * nxt, 16 + 2 * nxt);
+    }
   };
   // blocks [k0, k0 + check_every) with k0 even, k0 >= 2 and no last iteration inside are identical
   // launch sequences: capture once, replay
@@ -552,6 +524,8 @@ int cgcg_solve(pmgx_cg* s, pmgx_operator* A, double* x, const double* b, int che
     count_launch(c, s->graph_launches);
   };
   int k = 0;
+  co->last_converged = false;
+  co->last_rel = 0.0;
   while (k < s->max_iter)
   {
     if (block_ok && k >= 2 && k % check_every == 0 && k + check_every < s->max_iter && !s->graph_off)
@@ -574,8 +548,12 @@ int cgcg_solve(pmgx_cg* s, pmgx_operator* A, double* x, const double* b, int che
       const double r = c->h_scalars[16 + 2 * nxt];
       s->rnorm0 = c->h_scalars[22];
       s->history.push_back(r);
+      co->last_rel = s->rnorm0 > 0.0 ? std::sqrt(std::max(r, 0.0) / s->rnorm0) : 0.0;
       if (!(r > 0.0) || r / s->rnorm0 < rtol2)
+      {
+        co->last_converged = true;
         break;
+      }
     }
   }
   return k;
@@ -583,13 +561,6 @@ int cgcg_solve(pmgx_cg* s, pmgx_operator* A, double* x, const double* b, int che
 } // namespace pmgx
 
 // ------------------------------------------------------------------------ coarse solver --
-struct pmgx_coarse
-{
-  pmgx_ctx* ctx = nullptr;
-  pmgx_operator* A = nullptr;
-  pmgx_cg* cg = nullptr;
-  int last_iters = 0;
-};
 
 // ----------------------------------------------------------------------------- V-cycle --
 struct pmgx_vcycle
@@ -819,6 +790,8 @@ int pmgx_coarse_create(pmgx_ctx* ctx, pmgx_operator* A, int max_iter, double rto
   cs->cg->r.release(); // the coarse variant works in its own slab
   cs->cg->y.release();
   cs->cg->p.release();
+  if (const char* e = getenv("PMGX_COARSE_CHECK_EVERY"))
+    cs->check_every = std::max(atoi(e), 1);
   *out = cs.release();
   PMGX_API_END
 }
@@ -827,13 +800,23 @@ int pmgx_coarse_solve(pmgx_coarse* cs, double* x, const double* b, int* iters_h)
   PMGX_API_BEGIN
   PMGX_REQUIRE(cs && x && b, "coarse_solve: null argument");
   PMGX_CUDA(cudaSetDevice(cs->ctx->device));
-  const int k = pmgx::cgcg_solve(cs->cg, cs->A, x, b, 8, false);
+  const int k = pmgx::cgcg_solve(cs, x, b, false);
   cs->last_iters = k;
   if (iters_h)
     *iters_h = k;
   PMGX_API_END
 }
 int pmgx_coarse_last_iterations(pmgx_coarse* cs) { return cs ? cs->last_iters : -1; }
+int pmgx_coarse_last_status(pmgx_coarse* cs, int* converged_h, double* rel_residual_h)
+{
+  PMGX_API_BEGIN
+  PMGX_REQUIRE(cs, "coarse_last_status: null handle");
+  if (converged_h)
+    *converged_h = cs->last_converged ? 1 : 0;
+  if (rel_residual_h)
+    *rel_residual_h = cs->last_rel;
+  PMGX_API_END
+}
 
 int pmgx_coarse_destroy(pmgx_coarse* cs)
 {
@@ -841,6 +824,7 @@ int pmgx_coarse_destroy(pmgx_coarse* cs)
   if (cs)
   {
     pmgx_cg_destroy(cs->cg);
+    delete cs->M;
     delete cs;
   }
   PMGX_API_END
@@ -965,8 +949,7 @@ int pmgx_vcycle_apply(pmgx_vcycle* v, const double* b_in, double* u_inout, doubl
   const pmgx::ChebResidual post = literal_seq ? pmgx::CHEB_R_FULL : pmgx::CHEB_R_NONE;
   if (v->coarse && nl > 1)
   {
-    static const int every = getenv("PMGX_COARSE_CHECK_EVERY") ? atoi(getenv("PMGX_COARSE_CHECK_EVERY")) : 8;
-    v->coarse->last_iters = pmgx::cgcg_solve(v->coarse->cg, v->coarse->A, U[0], B[0], every, true); // :106-107 (u[0] = 0)
+    v->coarse->last_iters = pmgx::cgcg_solve(v->coarse, U[0], B[0], true); // :106-107 (u[0] = 0)
   }
   else
     pmgx::cheb_solve(v->smoothers[0], v->ops[0], U[0], B[0], nullptr, !literal_seq && nl > 1, post); // :109

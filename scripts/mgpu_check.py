@@ -157,7 +157,13 @@ def run_check(api, ctx, rank, world, n=(9, 8, 7), perturb=0.15, log=print):
         interps.append(api.Interpolator(ctx, a["P"], b["P"], a["dm"], b["dm"], a["sp"].n_owned + a["sp"].n_ghost,
                                         b["sp"].n_owned + b["sp"].n_ghost, mesh.lcells, mesh.bcells, a["halo"], b["halo"]))
     A0 = lv[0]["op"].to_csr()
-    coarse = api.CoarseSolverType(ctx, A0, 60, 1e-10)
+    # the coarse solver of the product: smoothed-aggregation PCG (distributed hierarchy; PMGX_CHECK_AMG=0:
+    # Jacobi-PCG).  Both reach 1e-10, so the cycle's iterates equal the oracle's (Jacobi-CG to 1e-10)
+    use_amg = os.environ.get("PMGX_CHECK_AMG", "1") != "0"
+    coarse = api.CoarseSolverType(ctx, A0, 60, 1e-10, amg=use_amg, min_coarse=40)
+    if rank == 0:
+        log(f"[mgpu x{world}] coarse solver: {'SA-AMG PCG' if use_amg else 'Jacobi-PCG'}, levels on rank 0 "
+            f"(rows, nnz, ghosts, dense): {coarse.levels()}")
     pmg = api.MultigridPreconditioner(ctx, [L["bc"] for L in lv], flags=2)
     pmg.set_solvers(smoothers)
     pmg.set_operators([L["op"] for L in lv])
@@ -189,6 +195,13 @@ def run_check(api, ctx, rank, world, n=(9, 8, 7), perturb=0.15, log=print):
         uo = np.zeros(O[-1]["nd"])
     for it in range(3):
         rn = pmg.apply(bvec, u, verbose=True)
+        conv, crel = coarse.last_status()
+        if rank == 0:
+            good = conv and coarse.last_iterations() <= (12 if use_amg else 60)
+            ok = ok and good
+            checks[f"V-cycle {it} coarse solve (iterations, converged, rel)"] = [coarse.last_iterations(), bool(conv), crel]
+            log(f"[mgpu x{world}] V-cycle {it} coarse solve: {coarse.last_iterations()} iterations, "
+                f"converged {conv}, rel. residual {crel:.2e}  {'ok' if good else 'FAIL'}")
         hg = pmg.diagnostics()
         ug = gather_owned(u, sp)
         if rank == 0:

@@ -204,7 +204,8 @@ def _build_hierarchy(ctx, mesh, degrees, nsmooth=2):
 
 
 @pytest.mark.parametrize("degrees,n,coarse", [((1, 3), (10, 10, 10), False), ((1, 3), (12, 12, 12), False),
-                                                ((1, 3), (6, 6, 6), True),
+                                                ((1, 3), (6, 6, 6), True), ((1, 3), (6, 6, 6), "amg"),
+                                                ((1, 3), (12, 12, 12), "amg"),
                                                 ((1, 2, 4), (4, 4, 4), False), ((1, 2, 4), (4, 4, 4), True)])
 def test_vcycle_history(ctx, degrees, n, coarse):
     """Config 1 (python_tests/pmg.py: 10^3 cells, P3->P1) and a 3-level P4->P2->P1 cycle: per-stage
@@ -219,7 +220,9 @@ def test_vcycle_history(ctx, degrees, n, coarse):
         A0 = oo.assemble_csr(ols[0].P, ols[0].dm, ols[0].G, ols[0].kappa, ols[0].bc, ols[0].nd)
         d0 = 1.0 / A0.diagonal()
         cs_o = lambda u0, b0: osol.cg(lambda v: A0 @ v, d0, u0, b0, 60, 1e-10)[0]
-        cs_g = api.CoarseSolverType(ctx, gls[0].op.to_csr(), 60, 1e-10)
+        # "amg": smoothed-aggregation PCG (min_coarse 100: a real multilevel hierarchy at 12^3); both coarse
+        # solvers converge to 1e-10, so the cycle's iterates agree with the oracle's Jacobi-CG ones
+        cs_g = api.CoarseSolverType(ctx, gls[0].op.to_csr(), 60, 1e-10, amg=(coarse == "amg"), min_coarse=100)
     pmg = api.MultigridPreconditioner(ctx, [g.bc for g in gls], flags=2)
     pmg.set_solvers(smoothers)
     pmg.set_operators([g.op for g in gls])
@@ -243,7 +246,7 @@ def test_vcycle_history(ctx, degrees, n, coarse):
 
 
 @pytest.mark.parametrize("degrees,n,coarse", [((1, 3), (6, 6, 6), True), ((1, 2, 4), (4, 4, 4), False),
-                                                ((1, 2, 4), (4, 5, 3), True)])
+                                                ((1, 2, 4), (4, 5, 3), True), ((1, 2, 4), (4, 5, 3), "amg")])
 @pytest.mark.parametrize("flags", [0, 4])
 def test_vcycle_default_and_literal_sequence_match_oracle(ctx, degrees, n, coarse, flags):
     """The production cycle (flags 0: the smoother's recurrence residual is restricted with the last
@@ -260,7 +263,7 @@ def test_vcycle_default_and_literal_sequence_match_oracle(ctx, degrees, n, coars
         A0 = oo.assemble_csr(ols[0].P, ols[0].dm, ols[0].G, ols[0].kappa, ols[0].bc, ols[0].nd)
         d0 = 1.0 / A0.diagonal()
         cs_o = lambda u0, b0: osol.cg(lambda v: A0 @ v, d0, u0, b0, 200, 1e-12)[0]
-        cs_g = api.CoarseSolverType(ctx, gls[0].op.to_csr(), 200, 1e-12)
+        cs_g = api.CoarseSolverType(ctx, gls[0].op.to_csr(), 200, 1e-12, amg=(coarse == "amg"))
     pmg = api.MultigridPreconditioner(ctx, [g.bc for g in gls], flags=flags)
     pmg.set_solvers(smoothers)
     pmg.set_operators([g.op for g in gls])
