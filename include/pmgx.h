@@ -210,6 +210,12 @@ int pmgx_cg_create(pmgx_ctx* ctx, int n_owned, int n_ghost, pmgx_cg** out);
 int pmgx_cg_set_max_iterations(pmgx_cg* s, int max_iter);
 int pmgx_cg_set_tolerance(pmgx_cg* s, double rtol);
 int pmgx_cg_store_coefficients(pmgx_cg* s, int on);
+/* M^-1 of the solve: NULL (default) = Jacobi, the operator's diag^-1 like src/cg.hpp:154,162,192;
+ * a V-cycle handle = MultigridPreconditioner::apply from a zero initial guess (src/pmg.hpp:56) in
+ * those two places -- the outer Krylov solver of SURVEY 8f-4.  The handle is borrowed; its top
+ * level must have the solver's vector layout.  Use a tight coarse-solver tolerance: a truncated
+ * inner Krylov solve is not a fixed linear operator. */
+int pmgx_cg_set_preconditioner(pmgx_cg* s, pmgx_vcycle* M);
 /* solve -> iteration count in *iters_h (the reference's return value). */
 int pmgx_cg_solve(pmgx_cg* s, pmgx_operator* A, double* x, const double* b, int* iters_h);
 /* alphas()/betas()/residual history as stored by the reference (:213-218); returns count. */
@@ -250,13 +256,14 @@ int pmgx_coarse_create_amg(pmgx_ctx* ctx, pmgx_operator* A_csr, int max_iter, do
                            int min_coarse, int max_levels, pmgx_coarse** out);
 int pmgx_coarse_solve(pmgx_coarse* cs, double* x, const double* b, int* iters_h);
 /* iterations of the most recent solve (stand-alone or inside pmgx_vcycle_apply); the host looks at
- * the residual every 8 (Jacobi) / 2 (AMG) iterations, so the count is a multiple of that or max_iter */
+ * the residual every 8 iterations with the Jacobi preconditioner (the count is a multiple of 8 or
+ * max_iter) and after every iteration with the AMG cycle */
 int pmgx_coarse_last_iterations(pmgx_coarse* cs);
 /* did the most recent solve reach rtol (1) or stop at max_iter (0); relative residual
  * sqrt(r.M^-1 r / r0.M^-1 r0) at the last host check.  Non-convergence is never silent. */
 int pmgx_coarse_last_status(pmgx_coarse* cs, int* converged_h, double* rel_residual_h);
 /* levels of the AMG hierarchy (1 for Jacobi) and, per level, out_h[0]=owned rows [1]=nnz(A_l)
- * [2]=ghosts [3]=1 if dense coarsest solve; operator complexity = sum nnz / nnz(A_0) */
+ * [2]=ghosts [3]=1 if dense coarsest solve [4]=nnz(P_l); operator complexity = sum nnz / nnz(A_0) */
 int pmgx_coarse_num_levels(pmgx_coarse* cs);
 int pmgx_coarse_level_info(pmgx_coarse* cs, int level, long long* out_h);
 /* one application of the preconditioner alone, u = M^-1 r (for tests) */

@@ -407,6 +407,14 @@ public:
   void set_max_iterations(int max_iter) { pmgx::check(pmgx_cg_set_max_iterations(_h, max_iter)); }
   void set_tolerance(double tolerance) { pmgx::check(pmgx_cg_set_tolerance(_h, tolerance)); }
   void store_coefficients(bool val) { pmgx::check(pmgx_cg_store_coefficients(_h, val)); }
+  /// M^-1 = one V-cycle of a MultigridPreconditioner instead of the operator's diag^-1
+  /// (src/cg.hpp:162,192); the reference only ever iterates its "preconditioner" (examples/pmg/main.cpp:362-367)
+  template <typename PMG>
+  void set_preconditioner(std::shared_ptr<PMG> pmg)
+  {
+    _pmg_keepalive = pmg;
+    pmgx::check(pmgx_cg_set_preconditioner(_h, pmg ? pmg->handle() : nullptr));
+  }
   std::vector<T> alphas() { return coeff(0); }
   std::vector<T> betas() { return coeff(1); }
   T residual() const
@@ -438,6 +446,7 @@ private:
     return which == 0 ? a : b;
   }
   std::shared_ptr<const pmgx::IndexMap> _map;
+  std::shared_ptr<void> _pmg_keepalive;
   pmgx_cg* _h = nullptr;
 };
 } // namespace dolfinx::acc
@@ -562,6 +571,13 @@ public:
       _last_rnorm = rnorm;
   }
   T last_residual_norm() const { return _last_rnorm; } // "rnorm after PMG" (:146-149)
+  /// C handle (built on first use) -- what CGSolver::set_preconditioner binds to
+  pmgx_vcycle* handle()
+  {
+    if (!_h)
+      build();
+    return _h;
+  }
 
 private:
   void build()

@@ -65,12 +65,16 @@ def tqli(d, e):
     return 0
 
 
-def cg(A, dinv, x, b, max_iter, rtol, dot=np.dot):
+def cg(A, dinv, x, b, max_iter, rtol, dot=np.dot, M=None):
     """Returns (x, iters, alphas, betas, rnorms, rnorm0).  ``rnorms`` holds the value of
-    r.M^-1 r after every iteration (also those not stored by the reference)."""
+    r.M^-1 r after every iteration (also those not stored by the reference).  ``M`` (callable
+    r -> M^-1 r) stands in the two places where the reference multiplies by diag^-1
+    (src/cg.hpp:162,192): the p-multigrid V-cycle as the preconditioner."""
+    if M is None:
+        M = lambda v: v * dinv
     y = A(x)
     r = b - y
-    p = r * dinv
+    p = M(r)
     rnorm0 = dot(p, r)
     rnorm = rnorm0
     rtol2 = rtol * rtol
@@ -83,7 +87,7 @@ def cg(A, dinv, x, b, max_iter, rtol, dot=np.dot):
         alpha = rnorm / dot(p, y)
         x = x + alpha * p
         r = r - alpha * y
-        y = r * dinv
+        y = M(r)
         rnorm_new = dot(r, y)
         beta = rnorm_new / rnorm
         rnorm = rnorm_new

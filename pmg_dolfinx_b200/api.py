@@ -393,6 +393,13 @@ class CGSolver:
     def store_coefficients(self, on):
         check(lib.pmgx_cg_store_coefficients(self.h, 1 if on else 0))
 
+    def set_preconditioner(self, pmg):
+        """M^-1 = one V-cycle of a MultigridPreconditioner (None: back to Jacobi)."""
+        if pmg is not None and pmg.h is None:
+            pmg._build()
+        self._pmg = pmg
+        check(lib.pmgx_cg_set_preconditioner(self.h, pmg.h if pmg is not None else None))
+
     def solve(self, A, x, b, verbose=False):
         k = ctypes.c_int()
         check(lib.pmgx_cg_solve(self.h, A.h, ptr(x.data), ptr(b.data), ctypes.addressof(k)))
@@ -479,10 +486,10 @@ class CoarseSolverType:
         return bool(c.value), r.value
 
     def levels(self):
-        """[(owned rows, nnz, ghosts, dense coarsest?)] of the hierarchy on this rank"""
+        """[(owned rows, nnz(A), ghosts, dense coarsest?, nnz(P))] of the hierarchy on this rank"""
         out = []
         for l in range(lib.pmgx_coarse_num_levels(self.h)):
-            v = np.zeros(4, dtype=np.int64)
+            v = np.zeros(5, dtype=np.int64)
             check(lib.pmgx_coarse_level_info(self.h, l, ptr(v)))
             out.append(tuple(int(t) for t in v))
         return out

@@ -100,10 +100,13 @@ struct AmgPrecond : Precond
     long long nnz = 0;
     pmgx_operator* A = nullptr;
     bool own_A = false;
+    pmgx_operator* A_lp = nullptr; // owned: reduced-storage twin used by the smoother (level 0 only)
     pmgx_halo* halo = nullptr; // owned (levels >= 1)
     pmgx_cheb* sm = nullptr;
     RectCsr P, R;              // to / from the next coarser level
     DevBuf<double> x, b;       // levels >= 1 (and the private b of a dense level)
+    DevBuf<double> x2, r2;     // second coarse visit of a W-cycle (levels >= 1)
+    long long nnz_p = 0;
     bool dense = false;
     int n_global = 0;
     DevBuf<double> inv;
@@ -112,6 +115,7 @@ struct AmgPrecond : Precond
   pmgx_ctx* ctx = nullptr;
   std::vector<Lv> lv;
   int nu = 2;
+  int gamma = 1; // cycle index below level 0: 1 = V, 2 = W (two coarse visits; the small levels are latency, not bandwidth)
 
   ~AmgPrecond() override
   {
@@ -119,6 +123,8 @@ struct AmgPrecond : Precond
     {
       if (L.sm)
         pmgx_cheb_destroy(L.sm);
+      if (L.A_lp)
+        pmgx_operator_destroy(L.A_lp);
       if (L.own_A && L.A)
         pmgx_operator_destroy(L.A);
       if (L.halo)
@@ -155,11 +161,20 @@ struct AmgPrecond : Precond
       return;
     }
     Lv& C = lv[l + 1];
-    cheb_solve(L.sm, L.A, x, b, nullptr, true, CHEB_R_FULL);          // pre-smoothing from x = 0; sm->r = b - A x
+    pmgx_operator* As = L.A_lp ? L.A_lp : L.A;
+    cheb_solve(L.sm, As, x, b, nullptr, true, CHEB_R_FULL);           // pre-smoothing from x = 0; sm->r = b - A x
     spmv_rect(ctx, C.n_owned, L.R.ptr.p, L.R.cols.p, L.R.vals.p, L.sm->r.p, C.b.p, false, 32); // b_c = P^T r
     cycle(l + 1, C.b.p, C.x.p);
-    spmv_rect(ctx, L.n_owned, L.P.ptr.p, L.P.cols.p, L.P.vals.p, C.x.p, x, true, 8);         // x += P x_c
-    cheb_solve(L.sm, L.A, x, b, nullptr, false, CHEB_R_NONE);         // post-smoothing (same polynomial: M is symmetric)
+    if (gamma == 2 && l + 2 < (int)lv.size())
+    {
+      // W-cycle: a second visit on the coarse residual, x_c += B_c (b_c - A_c x_c)  (symmetric: 2B - BAB)
+      C.A->apply(C.x.p, C.r2.p);
+      vec::axpy(ctx, C.r2.p, -1.0, C.r2.p, C.b.p, C.n_owned);
+      cycle(l + 1, C.r2.p, C.x2.p);
+      vec::axpy(ctx, C.x.p, 1.0, C.x2.p, C.x.p, C.n_owned);
+    }
+    spmv_rect(ctx, L.n_owned, L.P.ptr.p, L.P.cols.p, L.P.vals.p, C.x.p, x, true, 4);          // x += P x_c
+    cheb_solve(L.sm, As, x, b, nullptr, false, CHEB_R_NONE);          // post-smoothing (same polynomial: M is symmetric)
   }
 
   void apply(const double* r, double* u) override { cycle(0, r, u); }
@@ -249,6 +264,13 @@ int pmgx_coarse_create_amg(pmgx_ctx* ctx, pmgx_operator* A, int max_iter, double
   std::unique_ptr<AmgPrecond> M(new AmgPrecond());
   M->ctx = ctx;
   M->nu = nu;
+  // A/B switches (defaults are the measured winners)
+  int nu_coarse = nu;
+  if (const char* e = getenv("PMGX_AMG_NU_COARSE"))
+    nu_coarse = std::min(std::max(atoi(e), 1), 8);
+  if (const char* e = getenv("PMGX_AMG_GAMMA"))
+    M->gamma = atoi(e) == 2 ? 2 : 1;
+  const bool use_lp = !(getenv("PMGX_AMG_LP") && atoi(getenv("PMGX_AMG_LP")) == 0);
   const int nl = (int)H.levels.size();
   M->lv.resize((size_t)nl);
   for (int l = 0; l < nl; ++l)
@@ -278,12 +300,11 @@ int pmgx_coarse_create_amg(pmgx_ctx* ctx, pmgx_operator* A, int max_iter, double
         return rc;
       D.own_A = true;
       const size_t nt = (size_t)L.n_owned + L.n_ghost;
-      D.x.alloc(nt);
-      D.b.alloc(nt);
-      if (nt > 0)
+      for (auto* buf : {&D.x, &D.b, &D.x2, &D.r2})
       {
-        PMGX_CUDA(cudaMemsetAsync(D.x.p, 0, nt * sizeof(double), ctx->stream));
-        PMGX_CUDA(cudaMemsetAsync(D.b.p, 0, nt * sizeof(double), ctx->stream));
+        buf->alloc(nt);
+        if (nt > 0)
+          PMGX_CUDA(cudaMemsetAsync(buf->p, 0, nt * sizeof(double), ctx->stream));
       }
     }
     {
@@ -291,8 +312,13 @@ int pmgx_coarse_create_amg(pmgx_ctx* ctx, pmgx_operator* A, int max_iter, double
       if (rc != PMGX_OK)
         return rc;
       // a coarsest level that could not be inverted densely is smoothed harder instead
-      D.sm->max_iter = (last && !L.dense) ? 4 * nu : nu;
+      D.sm->max_iter = (last && !L.dense) ? 4 * nu : (l == 0 ? nu : nu_coarse);
     }
+    // level 0 is the only level that does not fit the L2: its smoother streams the matrix with FP32
+    // values and 16-bit column deltas (PMGX_AMG_LP=0: the FP64 matrix)
+    if (l == 0 && !last && use_lp)
+      D.A_lp = pmgx::make_lp(Ac);
+    D.nnz_p = L.P.nnz();
     if (!last)
     {
       D.P.upload(L.P, ctx->stream);
@@ -318,7 +344,7 @@ int pmgx_coarse_create_amg(pmgx_ctx* ctx, pmgx_operator* A, int max_iter, double
   if (rc != PMGX_OK)
     return rc;
   cs->M = M.release();
-  cs->check_every = 2;
+  cs->check_every = 1; // an iteration costs ~0.7 ms, a host look at r.M^-1 r ~10 us
   if (const char* e = getenv("PMGX_COARSE_CHECK_EVERY"))
     cs->check_every = std::max(atoi(e), 1);
   *out = cs;
@@ -342,6 +368,7 @@ int pmgx_coarse_level_info(pmgx_coarse* cs, int level, long long* out_h)
     out_h[1] = pmgx_csr_nnz(cs->A);
     out_h[2] = cs->A->n_ghost;
     out_h[3] = 0;
+    out_h[4] = 0;
   }
   else
   {
@@ -350,6 +377,7 @@ int pmgx_coarse_level_info(pmgx_coarse* cs, int level, long long* out_h)
     out_h[1] = L.nnz;
     out_h[2] = L.n_ghost;
     out_h[3] = L.dense ? 1 : 0;
+    out_h[4] = L.nnz_p;
   }
   PMGX_API_END
 }

@@ -108,6 +108,62 @@ __global__ void k_extract_diag_inv(int n_rows, const double* __restrict__ vals,
   dinv[i] = d;
 }
 
+// owned-column block with FP32 values and 16-bit column deltas (D16) or the FP64 matrix's 32-bit columns
+template <bool D16>
+__global__ void __launch_bounds__(ST)
+k_spmv_lp(int n_rows, const float* __restrict__ vals, const int32_t* __restrict__ beg, const int32_t* __restrict__ end,
+          const int16_t* __restrict__ dcol, const int32_t* __restrict__ cols, const double* __restrict__ x,
+          double* __restrict__ y)
+{
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = gt / LPR, lane = gt % LPR;
+  double s = 0.0;
+  if (row < n_rows)
+  {
+    const int e = end[row];
+    for (int j0 = beg[row] + lane; j0 < e; j0 += UNR * LPR)
+    {
+      int c[UNR];
+      float v[UNR];
+#pragma unroll
+      for (int t = 0; t < UNR; ++t)
+      {
+        const int jj = j0 + t * LPR;
+        const bool ok = jj < e;
+        c[t] = ok ? (D16 ? row + (int)__ldcs(dcol + jj) : __ldcs(cols + jj)) : -1;
+        v[t] = ok ? __ldcs(vals + jj) : 0.f;
+      }
+#pragma unroll
+      for (int t = 0; t < UNR; ++t)
+        if (c[t] >= 0)
+          s = fma((double)v[t], x[c[t]], s);
+    }
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1)
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (row < n_rows && lane == 0)
+    y[row] = s;
+}
+
+__global__ void k_make_lp(int n_rows, const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ off_diag,
+                          const int32_t* __restrict__ cols, const double* __restrict__ vals, float* __restrict__ v32,
+                          int16_t* __restrict__ d16, int* __restrict__ overflow)
+{
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = gt / LPR, lane = gt % LPR;
+  if (row >= n_rows)
+    return;
+  for (int j = row_ptr[row] + lane; j < row_ptr[row + 1]; j += LPR)
+  {
+    v32[j] = (float)vals[j];
+    const int d = cols[j] - row;
+    if (j < off_diag[row] && (d > 32767 || d < -32767))
+      atomicOr(overflow, 1);
+    d16[j] = (int16_t)d;
+  }
+}
+
 // rectangular product for the AMG transfer operators: same kernel body with LANES lanes per row
 template <int LANES, bool ACCUM>
 __global__ void __launch_bounds__(ST)
@@ -143,6 +199,13 @@ void spmv_rect(pmgx_ctx* c, int n_rows, const int32_t* row_ptr, const int32_t* c
       k_spmv_rect<32, true><<<grid, ST, 0, c->stream>>>(n_rows, vals, row_ptr, cols, x, y);
     else
       k_spmv_rect<32, false><<<grid, ST, 0, c->stream>>>(n_rows, vals, row_ptr, cols, x, y);
+  }
+  else if (lanes == 4)
+  {
+    if (accumulate)
+      k_spmv_rect<4, true><<<grid, ST, 0, c->stream>>>(n_rows, vals, row_ptr, cols, x, y);
+    else
+      k_spmv_rect<4, false><<<grid, ST, 0, c->stream>>>(n_rows, vals, row_ptr, cols, x, y);
   }
   else
   {
@@ -185,6 +248,70 @@ void CsrOperator::apply(double* x, double* y)
     check_launch("k_spmv_ghost_rows");
     count_launch(ctx);
   }
+}
+
+void CsrOperatorLP::apply(double* x, double* y)
+{
+  cudaSetDevice(ctx->device);
+  const int grid = (int)(((long long)n_owned * LPR + ST - 1) / ST);
+  if (n_ghost > 0)
+    vec::set(ctx, y + n_owned, n_ghost, 0.0);
+  if (halo)
+    halo_fwd_begin(halo, x);
+  if (n_owned > 0)
+  {
+    if (d16)
+      k_spmv_lp<true><<<grid, ST, 0, ctx->stream>>>(n_owned, vals32.p, src->row_ptr.p, src->off_diag.p, dcol16.p, nullptr, x, y);
+    else
+      k_spmv_lp<false><<<grid, ST, 0, ctx->stream>>>(n_owned, vals32.p, src->row_ptr.p, src->off_diag.p, nullptr, src->cols.p, x, y);
+    check_launch("k_spmv_lp");
+    count_launch(ctx);
+  }
+  if (halo)
+    halo_fwd_end(halo, x);
+  if (src->n_ghost_rows > 0)
+  {
+    // the (small) ghost-column block stays FP64
+    const int g2 = (int)(((long long)src->n_ghost_rows * LPR + ST - 1) / ST);
+    k_spmv_ghost_rows<<<g2, ST, 0, ctx->stream>>>(src->n_ghost_rows, src->ghost_rows.p, src->values.p, src->off_diag.p,
+                                                  src->row_ptr.p, src->cols.p, x, y);
+    check_launch("k_spmv_ghost_rows");
+    count_launch(ctx);
+  }
+}
+
+CsrOperatorLP* make_lp(CsrOperator* A)
+{
+  pmgx_ctx* c = A->ctx;
+  std::unique_ptr<CsrOperatorLP> L(new CsrOperatorLP());
+  L->ctx = c;
+  L->kind = pmgx_operator::CSR;
+  L->n_owned = A->n_owned;
+  L->n_ghost = A->n_ghost;
+  L->halo = A->halo;
+  L->src = A;
+  L->diag_inv.alloc((size_t)A->n_owned);
+  if (A->n_owned > 0)
+    PMGX_CUDA(cudaMemcpyAsync(L->diag_inv.p, A->diag_inv.p, (size_t)A->n_owned * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  const size_t nnz = (size_t)std::max<long long>(A->nnz, 1);
+  L->vals32.alloc(nnz);
+  L->dcol16.alloc(nnz);
+  DevBuf<int> ovf;
+  ovf.alloc(1);
+  PMGX_CUDA(cudaMemsetAsync(ovf.p, 0, sizeof(int), c->stream));
+  if (A->n_owned > 0)
+  {
+    k_make_lp<<<(int)(((long long)A->n_owned * LPR + ST - 1) / ST), ST, 0, c->stream>>>(
+        A->n_owned, A->row_ptr.p, A->off_diag.p, A->cols.p, A->values.p, L->vals32.p, L->dcol16.p, ovf.p);
+    check_launch("k_make_lp");
+  }
+  int o = 0;
+  PMGX_CUDA(cudaMemcpyAsync(&o, ovf.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  PMGX_CUDA(cudaStreamSynchronize(c->stream));
+  L->d16 = o == 0;
+  if (!L->d16)
+    L->dcol16.release();
+  return L.release();
 }
 
 void CsrOperator::finish_setup()

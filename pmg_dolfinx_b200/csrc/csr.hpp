@@ -17,4 +17,19 @@ struct CsrOperator : pmgx_operator
   void apply(double* x, double* y) override;
   void finish_setup(); // extracts diag^-1 (src/csr.hpp:101-112)
 };
+
+// Reduced-storage twin of a CsrOperator for use INSIDE a preconditioner (amg.cu, level 0): the same
+// matrix with FP32 values and, when every owned column lies within +-32767 of its row, 16-bit column
+// deltas -- 6 (or 8) bytes per non-zero instead of 12, on a kernel that is purely HBM-bound.  Vectors
+// stay FP64.  The rounded matrix is still symmetric, so a cycle smoothed with it is a (slightly
+// different) symmetric preconditioner; the Krylov operator itself is never replaced.
+struct CsrOperatorLP : pmgx_operator
+{
+  CsrOperator* src = nullptr; // borrowed: row_ptr, off_diag, ghost rows, FP64 ghost-column block, halo
+  bool d16 = false;
+  DevBuf<float> vals32;       // owned-column entries at their CSR positions
+  DevBuf<int16_t> dcol16;     // col - row (d16) ...
+  void apply(double* x, double* y) override;
+};
+CsrOperatorLP* make_lp(CsrOperator* A);
 } // namespace pmgx

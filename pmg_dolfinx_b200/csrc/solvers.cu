@@ -346,8 +346,61 @@ void cheb_solve(pmgx_cheb* s, pmgx_operator* A, double* x, const double* b, doub
 
 namespace pmgx
 {
+// CGSolver::solve with M^-1 = one p-multigrid V-cycle from a zero initial guess
+// (MultigridPreconditioner::apply, src/pmg.hpp:56-155) in the two places where src/cg.hpp:162,192
+// multiply by diag^-1 -- SURVEY 8f-4: "the class is named Preconditioner but the example only
+// iterates it".  Same order of operations, same break-before-store semantics (:206-218); the cycle
+// costs three orders of magnitude more than the vector updates, so they are left unfused.
+int cg_solve_pmg(pmgx_cg* s, pmgx_operator* A, double* x, const double* b)
+{
+  pmgx_ctx* c = s->ctx;
+  const long long n = s->n_owned;
+  const long long nt = (long long)s->n_owned + s->n_ghost;
+  auto precond = [&](const double* r, double* z)
+  {
+    vec::set(c, z, nt, 0.0); // apply(x = r, y = z) improves z: start from zero
+    const int rc = pmgx_vcycle_apply(s->precond, r, z, nullptr);
+    if (rc != PMGX_OK)
+      throw Error{rc};
+  };
+  s->history.clear();
+  A->apply(x, s->y.p);                                                           // :159
+  vec::axpy(c, s->r.p, -1.0, s->y.p, b, n);                                      // :160
+  precond(s->r.p, s->p.p);                                                       // :162
+  const double rnorm0 = vec::dot(c, s->p.p, s->r.p, n);                          // :164
+  s->rnorm0 = rnorm0;
+  double rnorm = rnorm0;
+  const double rtol2 = s->rtol * s->rtol;
+  int k = 0;
+  while (k < s->max_iter)
+  {
+    ++k;
+    A->apply(s->p.p, s->y.p);                                                    // :179
+    const double alpha = rnorm / vec::dot(c, s->p.p, s->y.p, n);                 // :182
+    vec::axpy(c, x, alpha, s->p.p, x, n);                                        // :186
+    vec::axpy(c, s->r.p, -alpha, s->y.p, s->r.p, n);                             // :189
+    precond(s->r.p, s->y.p);                                                     // :192
+    const double rnorm_new = vec::dot(c, s->r.p, s->y.p, n);                     // :195
+    const double beta = rnorm_new / rnorm;
+    rnorm = rnorm_new;
+    s->history.push_back(rnorm);
+    if (rnorm / rnorm0 < rtol2)                                                  // :206
+      break;
+    vec::axpy(c, s->p.p, beta, s->p.p, s->y.p, n);                               // :211
+    if (s->store)
+    {
+      s->alphas.push_back(alpha);
+      s->betas.push_back(beta);
+      s->residuals.push_back(rnorm);
+    }
+  }
+  return k;
+}
+
 int cg_solve(pmgx_cg* s, pmgx_operator* A, double* x, const double* b)
 {
+  if (s->precond)
+    return cg_solve_pmg(s, A, x, b);
   pmgx_ctx* c = s->ctx;
   const long long n = s->n_owned;
   const double* dinv = A->diag_inv.p;
@@ -421,10 +474,10 @@ int cgcg_solve(pmgx_coarse* co, double* x, const double* b, bool x_is_zero)
     if (nt > 0)
       PMGX_CUDA(cudaMemsetAsync(s->slab.p, 0, 5 * ntp * sizeof(double), c->stream));
     if (s->graph)
-    {
       cudaGraphExecDestroy(s->graph);
-      s->graph = nullptr;
-    }
+    if (s->graph_odd)
+      cudaGraphExecDestroy(s->graph_odd);
+    s->graph = s->graph_odd = nullptr;
   }
   double* const cr = s->slab.p;            // r
   double* const w = s->slab.p + ntp;       // w = A u
@@ -475,17 +528,22 @@ int cgcg_solve(pmgx_coarse* co, double* x, const double* b, bool x_is_zero)
   };
   // blocks [k0, k0 + check_every) with k0 even, k0 >= 2 and no last iteration inside are identical
   // launch sequences: capture once, replay
+  // (an odd block length alternates between two graphs, one per parity of the scalar slots)
   static const bool graphs_enabled = !(getenv("PMGX_COARSE_GRAPH") && atoi(getenv("PMGX_COARSE_GRAPH")) == 0);
-  const bool block_ok = graphs_enabled && !s->graph_off && check_every >= 2 && check_every % 2 == 0;
+  const bool block_ok = graphs_enabled && !s->graph_off && check_every >= 1;
   auto run_block = [&](int k0)
   {
     const void* key[3] = {A, x, reinterpret_cast<const void*>((size_t)check_every)};
-    if (s->graph && (s->graph_key[0] != key[0] || s->graph_key[1] != key[1] || s->graph_key[2] != key[2]))
+    if ((s->graph || s->graph_odd) && (s->graph_key[0] != key[0] || s->graph_key[1] != key[1] || s->graph_key[2] != key[2]))
     {
-      cudaGraphExecDestroy(s->graph);
-      s->graph = nullptr;
+      if (s->graph)
+        cudaGraphExecDestroy(s->graph);
+      if (s->graph_odd)
+        cudaGraphExecDestroy(s->graph_odd);
+      s->graph = s->graph_odd = nullptr;
     }
-    if (!s->graph)
+    cudaGraphExec_t& slot_graph = (k0 & 1) ? s->graph_odd : s->graph;
+    if (!slot_graph)
     {
       const long long l0 = c->launches;
       cudaGraph_t g = nullptr;
@@ -504,7 +562,7 @@ int cgcg_solve(pmgx_coarse* co, double* x, const double* b, bool x_is_zero)
         ok = (cudaStreamEndCapture(c->stream, &g) == cudaSuccess) && ok && g != nullptr;
       }
       if (ok)
-        ok = cudaGraphInstantiate(&s->graph, g, 0) == cudaSuccess;
+        ok = cudaGraphInstantiate(&slot_graph, g, 0) == cudaSuccess;
       if (g)
         cudaGraphDestroy(g);
       s->graph_launches = (int)(c->launches - l0);
@@ -512,7 +570,7 @@ int cgcg_solve(pmgx_coarse* co, double* x, const double* b, bool x_is_zero)
       if (!ok)
       {
         cudaGetLastError();
-        s->graph = nullptr;
+        slot_graph = nullptr;
         s->graph_off = true; // this configuration cannot be captured: plain launches from now on
         for (int k = k0; k < k0 + check_every; ++k)
           iterate(k);
@@ -520,7 +578,7 @@ int cgcg_solve(pmgx_coarse* co, double* x, const double* b, bool x_is_zero)
       }
       s->graph_key[0] = key[0], s->graph_key[1] = key[1], s->graph_key[2] = key[2];
     }
-    PMGX_CUDA(cudaGraphLaunch(s->graph, c->stream));
+    PMGX_CUDA(cudaGraphLaunch(slot_graph, c->stream));
     count_launch(c, s->graph_launches);
   };
   int k = 0;
@@ -685,6 +743,13 @@ int pmgx_cg_set_tolerance(pmgx_cg* s, double rtol)
   s->rtol = rtol;
   PMGX_API_END
 }
+int pmgx_cg_set_preconditioner(pmgx_cg* s, pmgx_vcycle* M)
+{
+  PMGX_API_BEGIN
+  PMGX_REQUIRE(s, "cg_set_preconditioner: null solver");
+  s->precond = M;
+  PMGX_API_END
+}
 int pmgx_cg_store_coefficients(pmgx_cg* s, int on)
 {
   PMGX_API_BEGIN
@@ -768,6 +833,8 @@ int pmgx_cg_destroy(pmgx_cg* s)
     cudaStreamSynchronize(s->ctx->stream);
     if (s->graph)
       cudaGraphExecDestroy(s->graph);
+    if (s->graph_odd)
+      cudaGraphExecDestroy(s->graph_odd);
     delete s;
   }
   PMGX_API_END

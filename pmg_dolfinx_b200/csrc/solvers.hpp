@@ -48,12 +48,13 @@ struct pmgx_cg
   int max_iter = 0;
   double rtol = 0.0;
   bool store = false;
+  pmgx_vcycle* precond = nullptr; // borrowed; null: Jacobi (diag^-1 of the operator, src/cg.hpp:154)
   pmgx::DevBuf<double> r, y, p; // src/cg.hpp:241-244
   pmgx::DevBuf<double> slab;    // r, w, p, u, s of the single-reduction coarse variant, contiguous (lazy)
   // CUDA graph of one block of `graph_len` coarse iterations (captured from the stream on first use,
   // replayed between the host's convergence checks): the ~8 small launches and 4 cross-stream
   // events of an iteration cost more in launch gaps than the kernels of a 1.6 M-dof level run
-  cudaGraphExec_t graph = nullptr;
+  cudaGraphExec_t graph = nullptr, graph_odd = nullptr; // blocks starting at an even / odd iteration
   const void* graph_key[3] = {nullptr, nullptr, nullptr}; // operator, x, block length
   int graph_launches = 0;
   bool graph_off = false;
@@ -78,7 +79,7 @@ struct pmgx_coarse
 namespace pmgx
 {
 int cgcg_solve(pmgx_coarse* cs, double* x, const double* b, bool x_is_zero);
-// rectangular CSR product y (=|+=) M x, `lanes` (8 or 32) lanes per row (csr.cu)
+// rectangular CSR product y (=|+=) M x, `lanes` (4, 8 or 32) lanes per row (csr.cu)
 void spmv_rect(pmgx_ctx* c, int n_rows, const int32_t* row_ptr, const int32_t* cols, const double* vals,
                const double* x, double* y, bool accumulate, int lanes);
 } // namespace pmgx

@@ -14,9 +14,14 @@ def main():
     d_bc = ctx.to_device(sp.bc)
     op = api.MatFreeLaplacian(ctx, 1, d_k, d_dm, d_x, d_g, m.lcells, m.bcells, d_bc, sp.n_owned, 0, None)
     A = op.to_csr()
-    cs = api.CoarseSolverType(ctx, A, 60, 1e-4)
+    import os
+    amg = os.environ.get("PROBE_AMG", "1") != "0"
+    nu = int(os.environ.get("PROBE_NU", "2"))
+    rtol = float(os.environ.get("PROBE_RTOL", "1e-5"))
+    cs = api.CoarseSolverType(ctx, A, 60, rtol, amg=amg, nu=nu)
     x, b, y = api.Vector(ctx, sp.n_owned), api.Vector(ctx, sp.n_owned), api.Vector(ctx, sp.n_owned)
     b.set(1.0)
+    b.data[: sp.n_owned] *= (1 - d_bc[: sp.n_owned].double())
     def timeit(fn, reps=20):
         for _ in range(3): fn()
         ctx.sync()
@@ -32,5 +37,6 @@ def main():
     t_cs = timeit(solve, reps=5)
     nnz = A.nnz()
     print(json.dumps(dict(n_rows=sp.n_owned, nnz=nnz, spmv_ms=t_spmv, spmv_gbs=(nnz * 12 + sp.n_owned * 24) / t_spmv / 1e6,
-                          coarse_ms=t_cs)))
+                          coarse_ms=t_cs, amg=amg, nu=nu, rtol=rtol, iterations=cs.last_iterations(), status=cs.last_status(),
+                          levels=cs.levels())))
 main()

@@ -12,7 +12,8 @@ class OracleLevel:
         self.dm = om.dofmap(mesh, P)
         self.bc = om.bc_marker(mesh, P)
         self.nd = om.num_dofs(mesh, P)
-        self.kappa = np.full(mesh.ncells, kappa)
+        # scalar, or one value per cell (cell_constants of src/laplacian.hpp:230)
+        self.kappa = np.full(mesh.ncells, kappa) if np.isscalar(kappa) else np.ascontiguousarray(kappa, dtype=np.float64)
         self.G, self.detJ = oo.geometry_factors(mesh.verts, mesh.geom_dofmap, P, literal_detj=literal_detj)
 
     def A(self, x):

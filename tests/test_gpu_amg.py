@@ -31,13 +31,19 @@ def _setup(ctx, n, min_coarse, nu=2, rtol=1e-8, max_iter=60):
     return api, proto, A, bc, nd, op, cs
 
 
+@pytest.mark.parametrize("lp", [False, True], ids=["fp64-matrix", "fp32-int16-smoother-matrix"])
 @pytest.mark.parametrize("n,nu", [(8, 2), (16, 2), (16, 1), (20, 3)])
-def test_device_cycle_equals_numpy_cycle_on_the_same_hierarchy(ctx, n, nu):
+def test_device_cycle_equals_numpy_cycle_on_the_same_hierarchy(ctx, n, nu, lp, monkeypatch):
+    """lp: the level-0 smoother streams the matrix with FP32 values and 16-bit column deltas (the default):
+    the cycle is then the exact cycle of a matrix rounded to FP32, i.e. equal to 1e-6 instead of 1e-10."""
     from test_amg_setup import _hierarchy
+    monkeypatch.setenv("PMGX_AMG_LP", "1" if lp else "0")
+    tol = 2e-6 if lp else 1e-10
     api, proto, A, bc, nd, op, cs = _setup(ctx, n, 100, nu=nu)
     levels = _hierarchy(A, min_coarse=100, max_levels=12)
     info = cs.levels()
     assert len(info) == len(levels) and info[-1][3] == 1
+    assert [i[4] for i in info[:-1]] == [l["P"].nnz for l in levels[:-1]]
     assert [i[0] for i in info] == [l["A"].shape[0] for l in levels]
     assert [i[1] for i in info] == [l["A"].nnz for l in levels]
     rng = np.random.default_rng(3)
@@ -47,14 +53,14 @@ def test_device_cycle_equals_numpy_cycle_on_the_same_hierarchy(ctx, n, nu):
     cs.apply_preconditioner(rv, uv)
     u = uv.data_copy()
     uo = proto.vcycle(levels, 0, r, nu)
-    assert np.linalg.norm(u - uo) <= 1e-10 * np.linalg.norm(uo)
+    assert np.linalg.norm(u - uo) <= tol * np.linalg.norm(uo)
     # M^-1 is symmetric (same Chebyshev polynomial before and after the coarse correction)
     s = rng.uniform(-1, 1, nd) * (~bc)
     sv, tv = api.Vector(ctx, nd), api.Vector(ctx, nd)
     sv.copy_from_host(s)
     cs.apply_preconditioner(sv, tv)
     a, b = float(np.dot(s, u)), float(np.dot(r, tv.data_copy()))
-    assert abs(a - b) <= 1e-10 * max(abs(a), abs(b))
+    assert abs(a - b) <= 1e-10 * max(abs(a), abs(b))   # exactly symmetric with the rounded matrix too
 
 
 @pytest.mark.parametrize("n", [12, 24])

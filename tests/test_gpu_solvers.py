@@ -172,9 +172,9 @@ def test_csr_assembly_and_spmv(ctx, P, perturb):
     assert rel(zv.data_copy(), Ao @ x)[0] < 1e-14
 
 
-def _build_hierarchy(ctx, mesh, degrees, nsmooth=2):
+def _build_hierarchy(ctx, mesh, degrees, nsmooth=2, kappa=2.0):
     from pmg_dolfinx_b200 import api
-    ols = [OracleLevel(mesh, P) for P in degrees]
+    ols = [OracleLevel(mesh, P, kappa=kappa) for P in degrees]
     gls = [GpuLevel(ctx, ol) for ol in ols]
     olev, smoothers = [], []
     for ol, gl in zip(ols, gls):
@@ -280,3 +280,65 @@ def test_vcycle_default_and_literal_sequence_match_oracle(ctx, degrees, n, coars
         assert abs(rn - ho[-1][2]) <= 1e-9 * ho[0][2]
         assert rel(u.data_copy(), uo)[0] < 1e-9
     assert np.array_equal(bv.data_copy(), b_before)      # the caller's b is never modified
+
+
+def _variable_kappa(mesh):
+    """A non-constant coefficient: one value per cell, a smooth factor-20 variation plus a seeded jitter."""
+    c = mesh.verts[mesh.geom_dofmap].mean(axis=1)
+    rng = np.random.default_rng(11)
+    return (1.0 + 19.0 * c[:, 0] * c[:, 1] + np.sin(7.0 * c[:, 2]) ** 2) * rng.uniform(0.8, 1.25, mesh.ncells)
+
+
+@pytest.mark.parametrize("degrees,n,perturb", [((1, 3), (10, 10, 10), 0.0), ((1, 2, 4), (4, 5, 3), 0.15)])
+def test_pmg_preconditioned_cg_matches_oracle(ctx, degrees, n, perturb):
+    """SURVEY 8f-4: CGSolver with M^-1 = MultigridPreconditioner::apply (src/cg.hpp:147-222 with the
+    V-cycle of src/pmg.hpp:56-155 where the reference multiplies by diag^-1), on config 1 (10^3 cells,
+    P3->P1) and on a perturbed 3-level P4->P2->P1 hierarchy, with a NON-CONSTANT kappa per cell.
+    alpha / beta / residual history to 1e-10, identical iteration count.  The coarse problem is solved
+    exactly on both sides (oracle: sparse LU like python_tests/pmg.py:136-141; product: the AMG
+    hierarchy's dense coarsest level), so the preconditioner is the same fixed linear operator."""
+    from pmg_dolfinx_b200 import api
+    mesh = om.create_box(*n, perturb=perturb)
+    kap = _variable_kappa(mesh)
+    assert kap.max() / kap.min() > 10
+    ols, gls, olev, smoothers, interps, pro, res = _build_hierarchy(ctx, mesh, degrees, kappa=kap)
+    top = ols[-1]
+    b = oo.rhs_collocated(mesh, top.P, oo.f_sines(2, 1, 3, 1.0), top.bc)
+    A0 = sp.csc_matrix(oo.assemble_csr(ols[0].P, ols[0].dm, ols[0].G, ols[0].kappa, ols[0].bc, ols[0].nd))
+    lu = spla.splu(A0)
+    cs_o = lambda u0, b0: lu.solve(b0)
+    M_o = lambda r: osol.vcycle(olev, pro, res, r, np.zeros(top.nd), coarse_solve=cs_o)
+    dinv = 1.0 / top.diag()
+    xo, ko, al, be, hist, r0 = osol.cg(top.A, dinv, np.zeros(top.nd), b, 30, 1e-8, M=M_o)
+    _, kj, *_ = osol.cg(top.A, dinv, np.zeros(top.nd), b, 500, 1e-8)
+    assert ko < 30 and ko * 3 < kj          # the V-cycle is a much better preconditioner than Jacobi
+
+    cs_g = api.CoarseSolverType(ctx, gls[0].op.to_csr(), 10, 1e-13, amg=True, min_coarse=5000)
+    assert len(cs_g.levels()) == 1          # dense inverse of the whole P1 level: an exact coarse solve
+    pmg = api.MultigridPreconditioner(ctx, [g.bc for g in gls])
+    pmg.set_solvers(smoothers)
+    pmg.set_operators([g.op for g in gls])
+    pmg.set_interpolators(interps)
+    pmg.set_coarse_solver(cs_g)
+    cg = api.CGSolver(ctx, top.nd, 0)
+    cg.set_max_iterations(30)
+    cg.set_tolerance(1e-8)
+    cg.store_coefficients(True)
+    cg.set_preconditioner(pmg)
+    x, bv = gls[-1].vec(), gls[-1].vec(b)
+    k = cg.solve(gls[-1].op, x, bv)
+    assert k == ko
+    g0, gh = cg.history()
+    assert abs(g0 - r0) <= HTOL * r0
+    assert len(gh) == len(hist) and np.all(np.abs(gh - hist) <= 1e-9 * np.abs(hist[0]) + HTOL * np.abs(hist))
+    assert np.all(np.abs(cg.alphas() - al) <= HTOL * np.abs(al))
+    assert np.all(np.abs(cg.betas() - be) <= HTOL * np.abs(be))
+    assert rel(x.data_copy(), xo)[0] < 1e-9
+    # and it solves the problem: residual of the assembled operator
+    Atop = oo.assemble_csr(top.P, top.dm, top.G, top.kappa, top.bc, top.nd)
+    assert np.linalg.norm(Atop @ x.data_copy() - b) <= 1e-6 * np.linalg.norm(b)
+    # back to Jacobi: the default path is untouched
+    cg.set_preconditioner(None)
+    x2 = gls[-1].vec()
+    cg.set_max_iterations(5)
+    assert cg.solve(gls[-1].op, x2, bv) == 5
