@@ -359,6 +359,12 @@ int pmgx_boxmesh_fit(long long ndofs_total, int order, int* nxyz_h);
  * evaluated by the caller: fvals[n_owned+n_ghost] device array of f at the dof coordinates.
  * Result is complete on owned dofs (ghost cells contribute, like the operator). */
 int pmgx_laplacian_rhs(pmgx_operator* lap, const double* fvals, double g, double* b);
+/* fem::apply_lifting + set_bc for inhomogeneous Dirichlet data (examples/pmg/main.cpp:293-295,
+ * examples/cg/main.cpp:235-237): b -= A_full g_bc on the owned rows, where A_full is this operator
+ * without its Dirichlet rows/columns and g_bc = gvals at the marked dofs, 0 elsewhere; then b = gvals at
+ * the marked dofs.  gvals[n_owned+n_ghost] (owned and ghost entries filled).  pmgx_laplacian_rhs calls
+ * this with the constant g whenever g != 0.  Set-up phase: builds a temporary un-constrained operator. */
+int pmgx_laplacian_lift(pmgx_operator* lap, const double* gvals, double* b);
 
 #ifdef __cplusplus
 }

@@ -220,16 +220,26 @@ def restrict(Pc, Pf, dm_c, dm_f, xf, nc, mult=None):
 # RHS (lumped GLL collocation; examples/pmg/poisson.py:30-40, main.cpp:289-295)
 # ---------------------------------------------------------------------------
 def rhs_collocated(mesh, P, f, bc, g=0.0, kappa=None, A=None):
-    """b_i = sum_{K contains i} f(x_i) w_i |detJ_K(x_i)|, then lifting (b -= A_full g) is
-    skipped for g == 0 and ``set_bc`` writes b = g at BC dofs."""
+    """fem::assemble_vector + apply_lifting + set_bc with the GLL rule (examples/pmg/main.cpp:289-295,
+    examples/cg/main.cpp:234-236):  b_i = sum_{K contains i} f(x_i) w_i |detJ_K(x_i)|, then the lifting
+    b -= A_full g_bc (A_full: the operator WITHOUT Dirichlet rows/columns, g_bc = g at BC dofs, 0 elsewhere;
+    DOLFINx apply_lifting with scale 1 and x0 = 0), then ``set_bc`` writes b = g at BC dofs.  ``g`` is a
+    scalar (the reference's constant 1.3, examples/cg/main.cpp:158) or one value per dof; ``kappa`` (scalar or
+    per cell) is only needed for g != 0 (default 2.0, examples/pmg/main.cpp:79)."""
     dm = omesh.dofmap(mesh, P)
     X = omesh.dof_coords(mesh, P)
-    _, detJ = geometry_factors(mesh.verts, mesh.geom_dofmap, P)
+    G, detJ = geometry_factors(mesh.verts, mesh.geom_dofmap, P)
     w = weights_3d(P)
     b = np.zeros(X.shape[0])
     fv = f(X)                                                       # [ndofs]
     np.add.at(b, dm.reshape(-1), (fv[dm] * (w[None, :] * np.abs(detJ))).reshape(-1))
-    b[bc != 0] = g
+    gv = np.full(X.shape[0], g, dtype=np.float64) if np.isscalar(g) else np.asarray(g, dtype=np.float64)
+    if np.any(gv[bc != 0] != 0.0):
+        kap = 2.0 if kappa is None else kappa
+        kap = np.full(mesh.ncells, kap) if np.isscalar(kap) else np.asarray(kap, dtype=np.float64)
+        gbc = np.where(bc != 0, gv, 0.0)
+        b -= apply(P, dm, G, kap, np.zeros_like(bc), gbc)           # A_full g_bc
+    b[bc != 0] = gv[bc != 0]
     return b
 
 

@@ -310,7 +310,12 @@ class MatFreeLaplacian(_Operator):
         return G.cpu().numpy().reshape(self.n_list, nq, 6)
 
     def assemble_rhs(self, fvals, g, b):
+        """assemble_vector + apply_lifting + set_bc (examples/pmg/main.cpp:289-295); g: constant BC value"""
         check(lib.pmgx_laplacian_rhs(self.h, ptr(fvals), float(g), ptr(b.data)))
+
+    def lift(self, gvals, b):
+        """b -= A_full g_bc on free rows, b = g on Dirichlet rows; gvals: device tensor (owned + ghost)"""
+        check(lib.pmgx_laplacian_lift(self.h, ptr(gvals), ptr(b.data)))
 
     def to_csr(self):
         return MatrixOperator._from_handle(self.ctx, lambda out: lib.pmgx_csr_from_laplacian(self.h, out))

@@ -306,6 +306,30 @@ __global__ void k_set_bc_value(double* __restrict__ b, const int8_t* __restrict_
     b[i] = g;
 }
 
+// gbc = bc ? g : 0
+__global__ void k_mask_to_bc(const double* __restrict__ g, const int8_t* __restrict__ bc, double* __restrict__ gbc, int n)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    gbc[i] = bc[i] ? g[i] : 0.0;
+}
+
+// b = bc ? g : b - y   (lifting on the free rows, set_bc on the marked ones)
+__global__ void k_lift(double* __restrict__ b, const double* __restrict__ y, const double* __restrict__ g,
+                       const int8_t* __restrict__ bc, int n)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    b[i] = bc[i] ? g[i] : y[i] * (-1.0) + b[i];
+}
+
+__global__ void k_fill(double* __restrict__ v, double a, int n)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    v[i] = a;
+}
+
 // ------------------------------------------------------------- CSR assembly kernels --
 // Entry (i,j) of the element matrix kappa * B^T G B with the collocated gradient table
 // (phi = identity at the GLL points, src/laplacian.hpp:200-202): only index pairs that
@@ -1666,6 +1690,7 @@ struct Laplacian : pmgx_operator
   const int8_t* bc = nullptr;    // borrowed
   const double* xgeom = nullptr;
   const int32_t* geom_dofmap = nullptr;
+  const int32_t* dofmap_borrowed = nullptr; // the caller's dofmap (borrowed like the reference's span, src/laplacian.hpp:502)
   int flags = 0;
   DevBuf<int32_t> perm; // launch position -> caller cell index (lcells then bcells)
   DevBuf<int32_t> enc;  // BC-encoded dofmap, layout `lay`
@@ -1800,6 +1825,7 @@ int pmgx_laplacian_create(pmgx_ctx* ctx, int degree, int n_cells, const int32_t*
   L->bc = bc_marker;
   L->xgeom = xgeom;
   L->geom_dofmap = geom_dofmap;
+  L->dofmap_borrowed = dofmap;
   L->flags = flags;
 
   const int n_list = L->n_list();
@@ -1963,12 +1989,63 @@ int pmgx_laplacian_rhs(pmgx_operator* op, const double* fvals, double g, double*
     pmgx::count_launch(ctx, 2);
     PMGX_CUDA(cudaStreamSynchronize(ctx->stream));
   }
-  if (ntot > 0)
+  if (ntot > 0 && g != 0.0)
+  {
+    // inhomogeneous data: b -= A_full g_bc, then set_bc (examples/pmg/main.cpp:293-295)
+    pmgx::DevBuf<double> gv;
+    gv.alloc((size_t)ntot);
+    pmgx::k_fill<<<(ntot + 255) / 256, 256, 0, ctx->stream>>>(gv.p, g, ntot);
+    pmgx::check_launch("k_fill");
+    const int rc = pmgx_laplacian_lift(op, gv.p, b);
+    if (rc != PMGX_OK)
+      return rc;
+    PMGX_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  else if (ntot > 0)
   {
     pmgx::k_set_bc_value<<<(ntot + 255) / 256, 256, 0, ctx->stream>>>(b, L->bc, g, ntot);
     pmgx::check_launch("k_set_bc_value");
     pmgx::count_launch(ctx);
   }
+  PMGX_API_END
+}
+
+int pmgx_laplacian_lift(pmgx_operator* op, const double* gvals, double* b)
+{
+  PMGX_API_BEGIN
+  PMGX_REQUIRE(op && op->kind == pmgx_operator::LAPLACIAN && gvals && b, "laplacian_lift: bad arguments");
+  auto* L = static_cast<Laplacian*>(op);
+  pmgx_ctx* ctx = L->ctx;
+  PMGX_CUDA(cudaSetDevice(ctx->device));
+  const int ntot = L->n_owned + L->n_ghost;
+  if (ntot == 0)
+    return PMGX_OK;
+  // the same cells, geometry and kappa with an all-zero Dirichlet marker: A_full.  No halo: g_bc is
+  // given on owned AND ghost dofs, and the ghost cells make the owned rows complete.
+  pmgx::DevBuf<int8_t> nobc;
+  nobc.alloc((size_t)ntot);
+  PMGX_CUDA(cudaMemsetAsync(nobc.p, 0, (size_t)ntot, ctx->stream));
+  std::vector<int32_t> perm_h((size_t)L->n_list());
+  if (!perm_h.empty())
+    PMGX_CUDA(cudaMemcpy(perm_h.data(), L->perm.p, perm_h.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  pmgx_operator* full = nullptr;
+  const int n_points_unknown = 0; // only used for argument checks
+  const int rc = pmgx_laplacian_create(ctx, L->P, L->n_cells, L->dofmap_borrowed, L->xgeom, n_points_unknown, L->geom_dofmap,
+                                       L->kappa, perm_h.data(), (int)perm_h.size(), nullptr, 0, nobc.p, L->n_owned,
+                                       L->n_ghost, nullptr, (L->flags & PMGX_LAP_LITERAL_DETJ) | PMGX_LAP_NO_DIAG, &full);
+  if (rc != PMGX_OK)
+    return rc;
+  pmgx::DevBuf<double> gbc, y;
+  gbc.alloc((size_t)ntot);
+  y.alloc((size_t)ntot);
+  pmgx::k_mask_to_bc<<<(ntot + 255) / 256, 256, 0, ctx->stream>>>(gvals, L->bc, gbc.p, ntot);
+  pmgx::check_launch("k_mask_to_bc");
+  full->apply(gbc.p, y.p);
+  pmgx::k_lift<<<(L->n_owned + 255) / 256, 256, 0, ctx->stream>>>(b, y.p, gvals, L->bc, L->n_owned);
+  pmgx::check_launch("k_lift");
+  pmgx::count_launch(ctx, 2);
+  PMGX_CUDA(cudaStreamSynchronize(ctx->stream));
+  pmgx_operator_destroy(full);
   PMGX_API_END
 }
 

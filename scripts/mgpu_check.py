@@ -176,6 +176,10 @@ def run_check(api, ctx, rank, world, n=(9, 8, 7), perturb=0.15, log=print):
     bvec = api.Vector(ctx, sp.n_owned, sp.n_ghost, top["halo"])
     top["op"].assemble_rhs(ctx.to_device(f), 0.0, bvec)
     bg = gather_owned(bvec, sp)
+    # inhomogeneous Dirichlet data: assemble + lifting + set_bc (examples/pmg/main.cpp:289-295)
+    blift = api.Vector(ctx, sp.n_owned, sp.n_ghost, top["halo"])
+    top["op"].assemble_rhs(ctx.to_device(f), 1.3, blift)
+    blg = gather_owned(blift, sp)
     u = api.Vector(ctx, sp.n_owned, sp.n_ghost)
     if rank == 0:
         from oracle import mesh as om, operator as oo, solvers as osol
@@ -192,6 +196,8 @@ def run_check(api, ctx, rank, world, n=(9, 8, 7), perturb=0.15, log=print):
         fo = 2.0 * np.pi ** 2 * 3 * np.sin(np.pi * Xo[:, 0]) * np.sin(np.pi * Xo[:, 1]) * np.sin(np.pi * Xo[:, 2]) + 1.0 + Xo[:, 0]
         bo = oo.rhs_collocated(omesh, degrees[-1], lambda _: fo, O[-1]["bc"])
         check("rhs assembly", bg, bo, 1e-13)
+        check("rhs assembly + lifting (g = 1.3)", blg,
+              oo.rhs_collocated(omesh, degrees[-1], lambda _: fo, O[-1]["bc"], g=1.3, kappa=2.0), 1e-12)
         uo = np.zeros(O[-1]["nd"])
     for it in range(3):
         rn = pmg.apply(bvec, u, verbose=True)

@@ -156,3 +156,43 @@ def test_affine_geometry_kernel_on_a_sheared_box(ctx, P):
     gl2 = GpuLevel(ctx, ol2)
     assert not gl2.op.is_affine()
     assert rel(gl2.apply(x), ol2.A(x))[1] < 1e-12
+
+
+@pytest.mark.parametrize("P,perturb", [(1, 0.0), (3, 0.2), (4, 0.0), (6, 0.15)])
+def test_rhs_with_lifting_matches_oracle_and_reproduces_constants(ctx, P, perturb):
+    """assemble_vector + apply_lifting + set_bc with inhomogeneous Dirichlet data g = 1.3
+    (examples/cg/main.cpp:158,234-236; examples/pmg/main.cpp:293-295): b equals the oracle's, and the
+    known answer -- with f = 0 the solution of A u = b is the constant g (constants are in the kernel of
+    the unconstrained operator) -- comes out of a CG solve."""
+    from pmg_dolfinx_b200 import api
+    import torch
+    mesh = om.create_box(4, 3, 5, perturb=perturb)
+    ol = OracleLevel(mesh, P, kappa=np.random.default_rng(3).uniform(0.5, 2.0, mesh.ncells))
+    gl = GpuLevel(ctx, ol)
+    X = om.dof_coords(mesh, P)
+    f = lambda Y: 1000.0 * np.exp(-((Y[:, 0] - 0.5) ** 2 + (Y[:, 1] - 0.5) ** 2) / 0.02)   # examples/cg/main.cpp:136-148
+    g = 1.3
+    bo = oo.rhs_collocated(mesh, P, f, ol.bc, g=g, kappa=ol.kappa)
+    bv = gl.vec()
+    gl.op.assemble_rhs(ctx.to_device(f(X)), g, bv)
+    assert rel(bv.data_copy(), bo)[0] < 1e-12
+    # lifting really changed the free rows next to the boundary
+    b0 = oo.rhs_collocated(mesh, P, f, ol.bc, g=0.0)
+    free = ol.bc == 0
+    assert np.linalg.norm((bo - b0)[free]) > 1e-3 * np.linalg.norm(b0[free])
+    # per-dof Dirichlet data through the vector entry point
+    gvec = np.where(ol.bc != 0, 1.0 + X[:, 0] - 2.0 * X[:, 2], 7.0)
+    bo2 = oo.rhs_collocated(mesh, P, f, ol.bc, g=gvec, kappa=ol.kappa)
+    bv2 = gl.vec()
+    gl.op.assemble_rhs(ctx.to_device(f(X)), 0.0, bv2)
+    gl.op.lift(ctx.to_device(gvec), bv2)
+    assert rel(bv2.data_copy(), bo2)[0] < 1e-12
+    # known answer: f = 0, g constant -> u = g
+    bz = gl.vec()
+    gl.op.assemble_rhs(ctx.to_device(np.zeros(ol.nd)), g, bz)
+    cg = api.CGSolver(ctx, ol.nd, 0)
+    cg.set_max_iterations(400)
+    cg.set_tolerance(1e-12)
+    u = gl.vec()
+    cg.solve(gl.op, u, bz)
+    assert np.abs(u.data_copy() - g).max() < 1e-8

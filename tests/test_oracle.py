@@ -205,3 +205,21 @@ def test_oracle_pmg_preconditioned_cg_solves_variable_kappa_problem():
     assert k < 40 and 3 * k < kj
     assert np.linalg.norm(x - xd) <= 1e-8 * np.linalg.norm(xd)
     assert np.all(np.diff(hist) < 0)            # monotone in the M^-1 norm: M^-1 is SPD
+
+
+@pytest.mark.parametrize("P", [1, 2, 4])
+def test_oracle_lifting_reproduces_the_dirichlet_extension(P):
+    """apply_lifting + set_bc (examples/pmg/main.cpp:293-295): with f = 0 and linear Dirichlet data on an
+    affine mesh the discrete solution is that linear field (it is in the kernel of the unconstrained
+    operator and in the discrete space), so A_bc u = b must hold for u = g."""
+    import scipy.sparse as sp
+    mesh = om.create_box(3, 4, 2)
+    dm, bc, nd = om.dofmap(mesh, P), om.bc_marker(mesh, P), om.num_dofs(mesh, P)
+    X = om.dof_coords(mesh, P)
+    gfield = 0.7 + 2.0 * X[:, 0] - 1.5 * X[:, 1] + 0.25 * X[:, 2]
+    kap = np.random.default_rng(0).uniform(1.0, 3.0, mesh.ncells) * 0 + 2.5   # constant: linear fields stay harmonic
+    b = oo.rhs_collocated(mesh, P, lambda Y: np.zeros(len(Y)), bc, g=gfield, kappa=kap)
+    G, _ = oo.geometry_factors(mesh.verts, mesh.geom_dofmap, P)
+    r = oo.apply(P, dm, G, np.full(mesh.ncells, 2.5), bc, gfield) - b
+    assert np.abs(r).max() <= 1e-12 * max(np.abs(b).max(), 1.0)
+    assert np.array_equal(b[bc != 0], gfield[bc != 0])
