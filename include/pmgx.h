@@ -49,6 +49,7 @@ typedef struct pmgx_interp pmgx_interp;
 typedef struct pmgx_coarse pmgx_coarse;
 typedef struct pmgx_vcycle pmgx_vcycle;
 typedef struct pmgx_boxmesh pmgx_boxmesh;
+typedef struct pmgx_ghostmesh pmgx_ghostmesh;
 typedef struct pmgx_amg_hier pmgx_amg_hier;
 
 /* ------------------------------------------------------------------ misc -- */
@@ -353,6 +354,31 @@ int pmgx_boxmesh_halo_lists(pmgx_boxmesh* m, int degree, int* send_ranks_h, int*
 /* Mesh-size fit of the drivers (examples/pmg/main.cpp:412-435): cells per direction whose
  * (n*order+1)^3 dof count is closest to ndofs_total. */
 int pmgx_boxmesh_fit(long long ndofs_total, int order, int* nxyz_h);
+
+/* ------------------------------------------- general mesh + ghost layer (host) -- */
+/* Ghost-layer builder for GENERAL conforming hexahedral meshes -- arbitrary vertex numbering, cell order,
+ * cell orientation and partition -- producing for `rank` the arrays the operator API takes, i.e. what
+ * the reference drivers get from DOLFINx (examples/pmg/main.cpp:199-256): ghost_layer_mesh (src/mesh.hpp:
+ * 16-98: every cell of another rank sharing a vertex with this rank's cells is ghosted),
+ * compute_boundary_cells (:105-143), tensor-product dofmaps per degree with edge/face dofs numbered in
+ * an orientation-independent frame, geometry + geometry dofmap (tp vertex order 4a+2b+c), the exterior-
+ * facet Dirichlet marker and the IndexMap/Scatterer lists.  Pure host code.  The whole mesh description
+ * is given on every rank: cell_vertices_h[n_cells][8] global vertex ids, cell_owner_h[n_cells] the
+ * partition, coords_h[n_vertices][3].  Accessors mirror pmgx_boxmesh_*; l2g_h holds library-global dof
+ * ids (vertices, then edges, faces, cell interiors); geometry's cell_gid_h[n_cells] the global cell id
+ * of every local cell (owned first). */
+int pmgx_ghostmesh_create(int rank, int nranks, long long n_cells, const long long* cell_vertices_h,
+                          const int* cell_owner_h, long long n_vertices, const double* coords_h,
+                          pmgx_ghostmesh** out);
+int pmgx_ghostmesh_destroy(pmgx_ghostmesh* m);
+int pmgx_ghostmesh_sizes(pmgx_ghostmesh* m, long long* out_h);
+int pmgx_ghostmesh_geometry(pmgx_ghostmesh* m, double* xgeom_h, int32_t* geom_dofmap_h, long long* cell_gid_h);
+int pmgx_ghostmesh_cell_lists(pmgx_ghostmesh* m, int32_t* lcells_h, int32_t* bcells_h);
+int pmgx_ghostmesh_space_sizes(pmgx_ghostmesh* m, int degree, long long* out_h);
+int pmgx_ghostmesh_space(pmgx_ghostmesh* m, int degree, int32_t* dofmap_h, int8_t* bc_h, long long* l2g_h,
+                         double* coords_h);
+int pmgx_ghostmesh_halo_lists(pmgx_ghostmesh* m, int degree, int* send_ranks_h, int* send_offsets_h,
+                              int32_t* send_idx_h, int* recv_ranks_h, int* recv_offsets_h, int32_t* recv_idx_h);
 
 /* GLL-collocated load vector b_i = sum_K f(x_i) w_i |detJ_K| followed by set_bc(b = g)
  * (fem::assemble_vector + set_bc with the GLL rule, examples/pmg/main.cpp:289-295). f is

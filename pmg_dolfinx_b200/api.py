@@ -146,6 +146,58 @@ class HostSpace:
     pass
 
 
+class GhostLayerMesh:
+    """General conforming hex mesh + partition -> this rank's arrays (pmgx_ghostmesh_*): the stand-in for
+    create_mesh + ghost_layer_mesh + compute_boundary_cells + dofmaps + BC marker + Scatterer lists of
+    examples/pmg/main.cpp:199-256 / src/mesh.hpp:16-143 for meshes that are not lexicographic boxes.
+    Same attribute surface as BoxMesh."""
+
+    def __init__(self, cell_vertices, cell_owner, coords, rank=0, nranks=1):
+        cv = _np(cell_vertices, np.int64).reshape(-1, 8)
+        ow = _np(cell_owner, np.int32)
+        xs = _np(coords, np.float64).reshape(-1, 3)
+        h = ctypes.c_void_p()
+        check(lib.pmgx_ghostmesh_create(rank, nranks, len(cv), ptr(cv), ptr(ow), len(xs), ptr(xs), ctypes.addressof(h)))
+        self.h, self.rank, self.nranks = h, rank, nranks
+        s = np.zeros(5, dtype=np.int64)
+        check(lib.pmgx_ghostmesh_sizes(self.h, ptr(s)))
+        self.n_cells, self.n_owned_cells, self.n_points, nl, nb = (int(v) for v in s)
+        self.xgeom = np.zeros((self.n_points, 3))
+        self.geom_dofmap = np.zeros((self.n_cells, 8), dtype=np.int32)
+        self.cell_gid = np.zeros(self.n_cells, dtype=np.int64)
+        check(lib.pmgx_ghostmesh_geometry(self.h, ptr(self.xgeom), ptr(self.geom_dofmap), ptr(self.cell_gid)))
+        self.lcells = np.zeros(nl, dtype=np.int32)
+        self.bcells = np.zeros(nb, dtype=np.int32)
+        check(lib.pmgx_ghostmesh_cell_lists(self.h, ptr(self.lcells), ptr(self.bcells)))
+
+    def space(self, degree, want_coords=True):
+        s = np.zeros(7, dtype=np.int64)
+        check(lib.pmgx_ghostmesh_space_sizes(self.h, degree, ptr(s)))
+        sp = HostSpace()
+        sp.degree = degree
+        (sp.n_owned, sp.n_ghost, nsn, nst, nrn, nrt, sp.n_global) = (int(v) for v in s)
+        nt = sp.n_owned + sp.n_ghost
+        sp.dofmap = np.zeros((self.n_cells, (degree + 1) ** 3), dtype=np.int32)
+        sp.bc = np.zeros(nt, dtype=np.int8)
+        sp.l2g = np.zeros(nt, dtype=np.int64)
+        sp.coords = np.zeros((nt, 3)) if want_coords else None
+        check(lib.pmgx_ghostmesh_space(self.h, degree, ptr(sp.dofmap), ptr(sp.bc), ptr(sp.l2g), ptr(sp.coords)))
+        sp.send_ranks = np.zeros(nsn, dtype=np.int32)
+        sp.send_offsets = np.zeros(nsn + 1, dtype=np.int32)
+        sp.send_idx = np.zeros(nst, dtype=np.int32)
+        sp.recv_ranks = np.zeros(nrn, dtype=np.int32)
+        sp.recv_offsets = np.zeros(nrn + 1, dtype=np.int32)
+        sp.recv_idx = np.zeros(nrt, dtype=np.int32)
+        check(lib.pmgx_ghostmesh_halo_lists(self.h, degree, ptr(sp.send_ranks), ptr(sp.send_offsets), ptr(sp.send_idx),
+                                            ptr(sp.recv_ranks), ptr(sp.recv_offsets), ptr(sp.recv_idx)))
+        return sp
+
+    def close(self):
+        if self.h:
+            lib.pmgx_ghostmesh_destroy(self.h)
+            self.h = None
+
+
 class Halo:
     """Forward-scatter plan = IndexMap + Scatterer of a reference Vector (src/vector.hpp:83-95)."""
 

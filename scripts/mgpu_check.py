@@ -29,7 +29,7 @@ def main():
     ctx = api.Context(local, rank, world, box[0])
     n = tuple(int(v) for v in os.environ.get("PMGX_CHECK_MESH", "9,8,7").split(","))
     perturb = float(os.environ.get("PMGX_CHECK_PERTURB", "0.15"))
-    res = run_check(api, ctx, rank, world, n, perturb)
+    res = run_check(api, ctx, rank, world, n, perturb, general=os.environ.get("PMGX_CHECK_GENERAL", "0") == "1")
     ctx.sync()
     dist.barrier()
     dist.destroy_process_group()
@@ -39,13 +39,24 @@ def main():
     sys.exit(0 if res["ok"] else 1)
 
 
-def run_check(api, ctx, rank, world, n=(9, 8, 7), perturb=0.15, log=print):
+def run_check(api, ctx, rank, world, n=(9, 8, 7), perturb=0.15, log=print, general=False):
     """Collective over all ranks of ctx (torch.distributed must be initialised when world > 1).
-    Returns {"ok", "max_rel", "max_err_over_tol", "transport", "checks"} on every rank."""
+    Returns {"ok", "max_rel", "max_err_over_tol", "transport", "checks"} on every rank.
+    general: the mesh is handed to the library as a GENERAL hex mesh -- vertices renumbered at random, cells
+    shuffled and rotated, partition along skew planes -- through the ghost-layer builder
+    (api.GhostLayerMesh, src/mesh.hpp:16-143) instead of the structured box partitioner."""
     degrees = (1, 2, 4)
-    mesh = api.BoxMesh(n, PGRID[world], rank, perturb=perturb)
-    # the same perturbed geometry for the oracle: take it from a single-domain product mesh
-    full = api.BoxMesh(n, (1, 1, 1), 0, perturb=perturb)
+    gen_oracle_mesh = None
+    if general:
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+        from test_ghostmesh import scrambled_box
+        gen_oracle_mesh, gcells, gowner, gcoords = scrambled_box(n, perturb, 5, world)
+        mesh = api.GhostLayerMesh(gcells, gowner, gcoords, rank, world)
+        full = mesh
+    else:
+        mesh = api.BoxMesh(n, PGRID[world], rank, perturb=perturb)
+        # the same perturbed geometry for the oracle: take it from a single-domain product mesh
+        full = api.BoxMesh(n, (1, 1, 1), 0, perturb=perturb)
 
     def gather_owned(vec, sp):
         """rank 0 gets the global vector in canonical numbering."""
@@ -75,6 +86,13 @@ def run_check(api, ctx, rank, world, n=(9, 8, 7), perturb=0.15, log=print):
     lv = []
     for P in degrees:
         sp = mesh.space(P, want_coords=True)
+        if general:
+            # canonical numbering = the structured oracle's, matched through the dof coordinates
+            from scipy.spatial import cKDTree
+            from oracle import mesh as om_
+            dd, idx = cKDTree(om_.dof_coords(gen_oracle_mesh, P)).query(sp.coords)
+            assert dd.max() < 1e-12
+            sp.l2g, sp.n_global = idx.astype(np.int64), om_.num_dofs(gen_oracle_mesh, P)
         halo = api.Halo.from_space(ctx, sp) if world > 1 else None
         dm, bc = ctx.to_device(sp.dofmap), ctx.to_device(sp.bc)
         op = api.MatFreeLaplacian(ctx, P, kappa, dm, xgeom, gdm, mesh.lcells, mesh.bcells, bc, sp.n_owned, sp.n_ghost, halo)
@@ -91,7 +109,7 @@ def run_check(api, ctx, rank, world, n=(9, 8, 7), perturb=0.15, log=print):
     ok = True
     if rank == 0:
         from oracle import mesh as om, operator as oo, solvers as osol
-        omesh = om.BoxMesh(n, full.xgeom.copy(), full.geom_dofmap.copy())
+        omesh = gen_oracle_mesh if general else om.BoxMesh(n, full.xgeom.copy(), full.geom_dofmap.copy())
         O = []
         for P in degrees:
             dm, bc, nd = om.dofmap(omesh, P), om.bc_marker(omesh, P), om.num_dofs(omesh, P)
@@ -223,7 +241,8 @@ def run_check(api, ctx, rank, world, n=(9, 8, 7), perturb=0.15, log=print):
     if world > 1:
         dist.broadcast_object_list(res, src=0)
     ctx.sync()
-    full.close()
+    if full is not mesh:
+        full.close()
     mesh.close()
     return res[0]
 

@@ -10,20 +10,24 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("p2p,perturb", [("1", "0.15"), ("0", "0.15"), ("1", "0.0")],
-                         ids=["nvlink-p2p", "nccl", "nvlink-p2p-affine-mesh"])
+@pytest.mark.parametrize("p2p,perturb,general", [("1", "0.15", "0"), ("0", "0.15", "0"), ("1", "0.0", "0"),
+                                                 ("1", "0.15", "1")],
+                         ids=["nvlink-p2p", "nccl", "nvlink-p2p-affine-mesh", "general-mesh-skew-partition"])
 @pytest.mark.parametrize("nranks", [2, 4, 8])
-def test_multi_gpu_matches_oracle(nranks, p2p, perturb):
+def test_multi_gpu_matches_oracle(nranks, p2p, perturb, general):
     import torch
     if not torch.cuda.is_available() or torch.cuda.device_count() < nranks:
         pytest.skip(f"needs {nranks} GPUs")
-    port = 29600 + nranks + 20 * int(p2p) + (40 if perturb == "0.0" else 0)
+    port = 29600 + nranks + 20 * int(p2p) + (40 if perturb == "0.0" else 0) + 80 * int(general)
     # "0": NCCL send/recv + ncclAllReduce instead of the peer-memory kernels; perturb 0: every cell is
     # affine, so the interior / boundary launches go through the affine-geometry kernel
-    env = dict(os.environ, PMGX_P2P=p2p, PMGX_CHECK_PERTURB=perturb)
+    # general: the mesh goes through the general ghost-layer builder (scrambled numbering, rotated cells, skew
+    # partition) instead of the structured box partitioner
+    env = dict(os.environ, PMGX_P2P=p2p, PMGX_CHECK_PERTURB=perturb, PMGX_CHECK_GENERAL=general)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nranks}",
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "scripts", "mgpu_check.py")]
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert f"[mgpu x{nranks}] PASS" in r.stdout
-    assert ("halo path: nvlink-p2p" if p2p == "1" else "halo path: nccl") in r.stdout
+    if general == "0":  # a skew partition may have one-sided neighbourhoods: those halos fall back to NCCL
+        assert ("halo path: nvlink-p2p" if p2p == "1" else "halo path: nccl") in r.stdout
