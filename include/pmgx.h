@@ -280,7 +280,7 @@ int pmgx_coarse_destroy(pmgx_coarse* cs);
  * this rank's owned dofs, columns >= n_owned address the ghosts of the forward-scatter plan given in
  * the pmgx_halo_create format; `allgather(user, mine, bytes, all)` must gather `bytes` bytes of every
  * rank into all[rank * bytes ...] and return 0 (the only collective the set-up uses).  Aggregates never
- * span ranks and the prolongator is smoothed with the rank-local part of A, so P_l is rank-local. */
+ * span ranks; the prolongator is smoothed with the full rows of A, so P_l has ghost columns. */
 typedef int (*pmgx_allgather_fn)(void* user, const void* mine, size_t bytes, void* all);
 int pmgx_amg_setup_h(int n_rows, const int32_t* row_ptr_h, const int32_t* cols_h, const double* values_h,
                      int min_coarse, int max_levels, pmgx_amg_hier** out);
@@ -291,8 +291,11 @@ int pmgx_amg_setup_dist_h(int rank, int nranks, int n_owned, int n_ghost, const 
                           pmgx_allgather_fn allgather, void* user, int min_coarse, int max_levels,
                           pmgx_amg_hier** out);
 /* out_h[0]=n_owned [1]=n_ghost [2]=n_send_nbr [3]=n_send [4]=n_recv_nbr [5]=n_recv
- * [6]=1 if this (coarsest) level holds rows of the dense inverse [7]=global rows of the level */
+ * [6]=1 if this (coarsest) level holds rows of the dense inverse [7]=global rows of the level [8]=nnz(R_l) */
 int pmgx_amg_level_dist_sizes(pmgx_amg_hier* h, int level, long long* out_h);
+/* R_l = the rows of the global P_l^T this rank owns: (columns of P_l that are owned) x (n_owned + n_ghost)
+ * CSR; with one rank R_l = P_l^T.  P_l's own columns >= its owned count address the next level's ghosts. */
+int pmgx_amg_level_get_restriction(pmgx_amg_hier* h, int level, int32_t* r_ptr_h, int32_t* r_cols_h, double* r_vals_h);
 /* ghost_src_h/ghost_rid_h[n_ghost]: owner rank and owner-local index of every ghost; halo plan of the
  * level; inv_rows_h[n_owned * n_global]: this rank's rows of the inverse of the gathered coarsest
  * matrix, columns ordered [owned | other ranks' entries in rank order].  Any pointer may be NULL. */

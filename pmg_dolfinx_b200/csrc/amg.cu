@@ -4,8 +4,9 @@
 // The hierarchy comes from amg_setup.cpp (host, collective).  Everything the cycle runs already exists
 // in this library: the CSR SpMV with its owned/ghost column split and overlapped halo (csr.cu), the
 // 4th-kind Chebyshev/Jacobi smoother with its dead-iteration elimination (solvers.cu), the
-// peer-memory halo (halo.cu).  Prolongation and restriction are rank-local rectangular CSR products
-// (P and an explicitly stored P^T: a gather, so the restriction is deterministic); the coarsest level
+// peer-memory halo (halo.cu).  Prolongation and restriction are rectangular CSR products (P and the owned
+// rows of P^T, stored explicitly: a gather, so the restriction is deterministic) behind one forward halo
+// update each, because the smoothed prolongator reaches across partition interfaces; the coarsest level
 // is gathered with an all-to-all halo plan and multiplied by this rank's rows of the dense inverse.
 // One V(nu,nu) cycle: per level 2 nu SpMVs + 2 transfers, no host synchronisation anywhere, so the
 // coarse PCG captures whole iterations into a CUDA graph (solvers.cu, cgcg_solve).
@@ -56,29 +57,6 @@ struct RectCsr
   }
 };
 
-amg::Csr transpose_host(const amg::Csr& A)
-{
-  amg::Csr T;
-  T.n_rows = A.n_cols;
-  T.n_cols = A.n_rows;
-  T.ptr.assign((size_t)A.n_cols + 1, 0);
-  for (int32_t c : A.cols)
-    ++T.ptr[c + 1];
-  for (size_t i = 1; i < T.ptr.size(); ++i)
-    T.ptr[i] += T.ptr[i - 1];
-  T.cols.resize(A.cols.size());
-  T.vals.resize(A.vals.size());
-  std::vector<int32_t> next(T.ptr.begin(), T.ptr.end() - 1);
-  for (int i = 0; i < A.n_rows; ++i)
-    for (int32_t j = A.ptr[i]; j < A.ptr[i + 1]; ++j)
-    {
-      const int32_t p = next[A.cols[j]]++;
-      T.cols[p] = i;
-      T.vals[p] = A.vals[j];
-    }
-  return T;
-}
-
 pmgx_halo* make_halo(pmgx_ctx* c, int n_owned, int n_ghost, const amg::Plan& p)
 {
   if (c->nranks == 1)
@@ -102,6 +80,7 @@ struct AmgPrecond : Precond
     bool own_A = false;
     pmgx_operator* A_lp = nullptr; // owned: reduced-storage twin used by the smoother (level 0 only)
     pmgx_halo* halo = nullptr; // owned (levels >= 1)
+    pmgx_halo* halo_v = nullptr; // borrowed: forward-scatter plan of this level's vectors (level 0: the operator's)
     pmgx_cheb* sm = nullptr;
     RectCsr P, R;              // to / from the next coarser level
     DevBuf<double> x, b;       // levels >= 1 (and the private b of a dense level)
@@ -163,6 +142,11 @@ struct AmgPrecond : Precond
     Lv& C = lv[l + 1];
     pmgx_operator* As = L.A_lp ? L.A_lp : L.A;
     cheb_solve(L.sm, As, x, b, nullptr, true, CHEB_R_FULL);           // pre-smoothing from x = 0; sm->r = b - A x
+    if (L.halo_v) // the rows of P^T this rank owns reach into the neighbours' fine dofs
+    {
+      halo_fwd_begin(L.halo_v, L.sm->r.p);
+      halo_fwd_end(L.halo_v, L.sm->r.p);
+    }
     spmv_rect(ctx, C.n_owned, L.R.ptr.p, L.R.cols.p, L.R.vals.p, L.sm->r.p, C.b.p, false, 32); // b_c = P^T r
     cycle(l + 1, C.b.p, C.x.p);
     if (gamma == 2 && l + 2 < (int)lv.size())
@@ -172,6 +156,11 @@ struct AmgPrecond : Precond
       vec::axpy(ctx, C.r2.p, -1.0, C.r2.p, C.b.p, C.n_owned);
       cycle(l + 1, C.r2.p, C.x2.p);
       vec::axpy(ctx, C.x.p, 1.0, C.x2.p, C.x.p, C.n_owned);
+    }
+    if (C.halo_v) // ... and P interpolates from the neighbours' aggregates
+    {
+      halo_fwd_begin(C.halo_v, C.x.p);
+      halo_fwd_end(C.halo_v, C.x.p);
     }
     spmv_rect(ctx, L.n_owned, L.P.ptr.p, L.P.cols.p, L.P.vals.p, C.x.p, x, true, 4);          // x += P x_c
     cheb_solve(L.sm, As, x, b, nullptr, false, CHEB_R_NONE);          // post-smoothing (same polynomial: M is symmetric)
@@ -282,10 +271,14 @@ int pmgx_coarse_create_amg(pmgx_ctx* ctx, pmgx_operator* A, int max_iter, double
     D.nnz = L.A.nnz();
     const bool last = l + 1 == nl;
     if (l == 0)
+    {
       D.A = A; // the caller's operator and halo
+      D.halo_v = Ac->halo;
+    }
     else
     {
       D.halo = pmgx::make_halo(ctx, L.n_owned, L.n_ghost, L.plan); // collective: same order on every rank
+      D.halo_v = D.halo;
       std::vector<int32_t> off((size_t)L.n_owned);
       for (int i = 0; i < L.n_owned; ++i)
       {
@@ -322,7 +315,7 @@ int pmgx_coarse_create_amg(pmgx_ctx* ctx, pmgx_operator* A, int max_iter, double
     if (!last)
     {
       D.P.upload(L.P, ctx->stream);
-      D.R.upload(pmgx::transpose_host(L.P), ctx->stream);
+      D.R.upload(L.R, ctx->stream);
     }
     else if (L.dense)
     {

@@ -3,12 +3,14 @@
 //
 // Distribution model (one rank per GPU, rows = owned dofs, columns = owned + ghost, exactly the
 // layout of acc::MatrixOperator, src/csr.hpp:57-131):
-//   * aggregates never span ranks and the prolongator is smoothed with the rank-local part of A
-//     (ghost couplings lumped onto the diagonal, so constants are still reproduced): P is block
-//     diagonal over the ranks, prolongation and restriction need no communication at all;
-//   * the Galerkin product A_c = P^T A P then only needs the prolongator rows of the ghost dofs
-//     (one exchange of sparse rows at set-up); A_c has the same owned-rows / ghost-columns layout
-//     with a halo plan of its own, so the construction recurses;
+//   * aggregates never span ranks, but the prolongator is smoothed with the full rows of A, so a row
+//     next to a partition interface also interpolates from the neighbour's aggregates (P has ghost
+//     columns; its transpose is stored as R over owned + ghost fine columns): prolongation needs a
+//     forward halo update of the coarse vector, restriction one of the fine residual;
+//   * the Galerkin product A_c = P^T A P needs the prolongator rows of the ghost dofs (one exchange of
+//     sparse rows at set-up) and returns partial rows of the neighbours' aggregates to their owners
+//     (a second one); A_c has the same owned-rows / ghost-columns layout with a halo plan of its own
+//     (covering the ghost aggregates A_c or P reference), so the construction recurses;
 //   * the coarsest level is gathered and inverted densely on every rank (each keeps its own rows).
 #pragma once
 #include <cstddef>
@@ -49,7 +51,8 @@ struct Level
   int n_owned = 0, n_ghost = 0;
   Csr A;    // n_owned rows; columns < n_owned are owned, the rest address ghosts; rows sorted by column
   Plan plan;
-  Csr P;    // n_owned x (owned dofs of the next level); empty on the coarsest level
+  Csr P;    // n_owned x (owned + ghost dofs of the next level); empty on the coarsest level
+  Csr R;    // (owned dofs of the next level) x (n_owned + n_ghost): the rows of the global P^T this rank owns
   double lmax = 1.0; // 1.1 * lambda_max(D^-1 A), power iteration
   std::vector<int> ghost_src;      // per ghost: owning rank
   std::vector<int32_t> ghost_rid;  // per ghost: index on the owning rank

@@ -7,10 +7,11 @@
 // Per level: greedy (Vanek) aggregation on the rank-local graph of the free rows (rows that hold
 // only their diagonal -- Dirichlet rows, src/csr.hpp:84-86 -- stay out of the hierarchy), tentative
 // prolongator T (piecewise constant), lambda_max(D^-1 A) by distributed power iteration (x1.1),
-// P = (I - 4/(3 lmax) D^-1 A_loc) T with A_loc = owned-column block of A, ghost couplings lumped
-// onto the diagonal; exchange of the P rows of the interface dofs; A_c = P^T A [P; P_ghost] by
-// row-wise SpGEMM; coarse halo plan from the ghost aggregates that A_c references.  Recursion stops
-// at min_coarse free rows (globally) or max_levels; the last level is gathered and inverted densely.
+// P = (I - 4/(3 lmax) D^-1 A) T with the full rows of A (exchange of the aggregate ids of the ghost dofs),
+// exchange of the P rows of the interface dofs, A_c = P^T A [P; P_ghost] by row-wise SpGEMM with the partial
+// rows of foreign aggregates returned to their owners, R = the owned rows of the global P^T, coarse halo plan
+// from the ghost aggregates that A_c or P reference.  Recursion stops at min_coarse free rows (globally) or
+// max_levels; the last level is gathered and inverted densely.
 // Sized and checked against scripts/prototype_sa_amg.py (tests/test_amg_setup.py, tests/test_dist_cpu.py).
 #include "common.hpp"
 #include "amg.hpp"
@@ -532,82 +533,91 @@ void setup(Hierarchy& H, Csr A0, int n_owned, int n_ghost, const Plan& plan0, co
       H.levels.push_back(std::move(L));
       break;
     }
-    // tentative prolongator T and the rank-local filtered matrix A_loc (ghost couplings lumped onto
-    // the diagonal: A_loc 1 = A 1, so P still reproduces constants next to a partition interface)
-    Csr T, Aloc;
-    T.n_rows = n, T.n_cols = na;
-    T.ptr.assign((size_t)n + 1, 0);
-    Aloc.n_rows = n, Aloc.n_cols = n;
-    Aloc.ptr.assign((size_t)n + 1, 0);
-    for (int i = 0; i < n; ++i)
+    // ---- smoothed prolongator P = (I - omega D^-1 A) T with the FULL rows of A: aggregates are rank-local,
+    // but a row next to a partition interface also interpolates from the neighbour's aggregates (with the
+    // rank-local part of A only, the interface behaves like unsmoothed aggregation: 18 instead of ~10 PCG
+    // iterations on 8 ranks).  Coarse unknowns are named by (owner rank, owner-local aggregate id) on the wire.
+    using Key = std::pair<int, int32_t>;
+    std::map<Key, int32_t> gmap; // ghost aggregates seen so far -> provisional local id (>= na, in discovery order)
+    std::vector<Key> gkeys;
+    auto local_id = [&](int owner, int32_t id) -> int32_t
     {
-      if (agg[i] >= 0)
+      if (owner == cm.rank)
+        return id;
+      auto it = gmap.find({owner, id});
+      if (it == gmap.end())
       {
-        T.cols.push_back(agg[i]);
-        T.vals.push_back(1.0);
+        it = gmap.emplace(Key{owner, id}, (int32_t)(na + (int)gkeys.size())).first;
+        gkeys.push_back({owner, id});
       }
-      T.ptr[i + 1] = (int32_t)T.cols.size();
-      double lump = 0.0;
-      size_t dpos = (size_t)-1;
-      for (int32_t j = M.ptr[i]; j < M.ptr[i + 1]; ++j)
+      return it->second;
+    };
+    auto key_of = [&](int32_t c) -> Key { return c < na ? Key{cm.rank, c} : gkeys[(size_t)(c - na)]; };
+    // aggregate of every ghost dof: the owners send agg[] of the dofs on their send lists
+    std::vector<int32_t> gagg((size_t)L.n_ghost, -1);
+    if (cm.nranks > 1)
+    {
+      std::vector<std::vector<char>> msgs(L.plan.send_ranks.size());
+      for (size_t k = 0; k < L.plan.send_ranks.size(); ++k)
+        for (int t = L.plan.send_offsets[k]; t < L.plan.send_offsets[k + 1]; ++t)
+          put1<int32_t>(msgs[k], agg[L.plan.send_idx[t]]);
+      for (auto& m : neighbor_exchange(cm, L.plan.send_ranks, msgs))
       {
-        if (M.cols[j] >= n)
-        {
-          lump += M.vals[j];
+        const auto it = std::find(L.plan.recv_ranks.begin(), L.plan.recv_ranks.end(), m.first);
+        if (it == L.plan.recv_ranks.end())
           continue;
+        const size_t k = it - L.plan.recv_ranks.begin();
+        Reader rd{m.second.data(), m.second.data() + m.second.size()};
+        for (int t = L.plan.recv_offsets[k]; t < L.plan.recv_offsets[k + 1]; ++t)
+        {
+          const int32_t a = rd.get1<int32_t>();
+          gagg[L.plan.recv_idx[t]] = a < 0 ? -1 : local_id(m.first, a);
         }
-        if (M.cols[j] == i)
-          dpos = Aloc.cols.size();
-        Aloc.cols.push_back(M.cols[j]);
-        Aloc.vals.push_back(M.vals[j]);
       }
-      if (dpos != (size_t)-1)
-        Aloc.vals[dpos] += lump;
-      Aloc.ptr[i + 1] = (int32_t)Aloc.cols.size();
     }
-    Csr AT = spgemm(Aloc, T);
+    // T over owned + ghost rows (at most one entry per row), then P for the owned rows
     const double omega = 4.0 / (3.0 * L.lmax);
     Csr P;
     P.n_rows = n;
-    P.n_cols = na;
     P.ptr.assign((size_t)n + 1, 0);
-    for (int i = 0; i < n; ++i)
     {
-      // merge row i of T (at most one entry) with -omega/d_i * row i of AT (sorted)
-      const int32_t tc = agg[i];
-      bool t_done = tc < 0;
-      for (int32_t j = AT.ptr[i]; j < AT.ptr[i + 1]; ++j)
+      std::vector<std::pair<int32_t, double>> row;
+      for (int i = 0; i < n; ++i)
       {
-        const int32_t c = AT.cols[j];
-        double v = -omega / d[i] * AT.vals[j];
-        if (!t_done && tc < c)
+        row.clear();
+        if (agg[i] >= 0)
+          row.emplace_back(agg[i], 1.0);
+        if (is_free[i])
+          for (int32_t j = M.ptr[i]; j < M.ptr[i + 1]; ++j)
+          {
+            const int32_t cj = M.cols[j];
+            const int32_t a = cj < n ? agg[cj] : gagg[cj - n];
+            if (a >= 0)
+              row.emplace_back(a, -omega / d[i] * M.vals[j]);
+          }
+        std::sort(row.begin(), row.end(), [](const std::pair<int32_t, double>& x, const std::pair<int32_t, double>& y)
+                  { return x.first < y.first; });
+        for (size_t t = 0; t < row.size(); ++t)
         {
-          P.cols.push_back(tc);
-          P.vals.push_back(1.0);
-          t_done = true;
+          if (!P.cols.empty() && (int32_t)P.cols.size() > P.ptr[i] && P.cols.back() == row[t].first)
+            P.vals.back() += row[t].second;
+          else
+          {
+            P.cols.push_back(row[t].first);
+            P.vals.push_back(row[t].second);
+          }
         }
-        if (!t_done && tc == c)
-        {
-          v += 1.0;
-          t_done = true;
-        }
-        P.cols.push_back(c);
-        P.vals.push_back(v);
+        P.ptr[i + 1] = (int32_t)P.cols.size();
       }
-      if (!t_done)
-      {
-        P.cols.push_back(tc);
-        P.vals.push_back(1.0);
-      }
-      P.ptr[i + 1] = (int32_t)P.cols.size();
     }
-    // prolongator rows of my ghosts: the owners send the rows of the dofs on their send lists
-    struct GhostRow
+    // prolongator rows of my ghost dofs: the owners send the rows of the dofs on their send lists, every
+    // column as (owner, id)
+    struct SRow
     {
-      std::vector<int32_t> cols; // owner-local aggregate ids
+      std::vector<int32_t> cols;
       std::vector<double> vals;
     };
-    std::vector<GhostRow> grow((size_t)L.n_ghost);
+    std::vector<SRow> grow((size_t)L.n_ghost);
     if (cm.nranks > 1)
     {
       std::vector<std::vector<char>> msgs(L.plan.send_ranks.size());
@@ -617,8 +627,13 @@ void setup(Hierarchy& H, Csr A0, int n_owned, int n_ghost, const Plan& plan0, co
           const int32_t i = L.plan.send_idx[t];
           const int32_t len = P.ptr[i + 1] - P.ptr[i];
           put1<int32_t>(msgs[k], len);
-          put(msgs[k], P.cols.data() + P.ptr[i], (size_t)len);
-          put(msgs[k], P.vals.data() + P.ptr[i], (size_t)len);
+          for (int32_t j = P.ptr[i]; j < P.ptr[i + 1]; ++j)
+          {
+            const Key kk = key_of(P.cols[j]);
+            put1<int32_t>(msgs[k], kk.first);
+            put1<int32_t>(msgs[k], kk.second);
+            put1<double>(msgs[k], P.vals[j]);
+          }
         }
       for (auto& m : neighbor_exchange(cm, L.plan.send_ranks, msgs))
       {
@@ -629,72 +644,168 @@ void setup(Hierarchy& H, Csr A0, int n_owned, int n_ghost, const Plan& plan0, co
         Reader rd{m.second.data(), m.second.data() + m.second.size()};
         for (int t = L.plan.recv_offsets[k]; t < L.plan.recv_offsets[k + 1]; ++t)
         {
-          GhostRow& g = grow[L.plan.recv_idx[t]];
+          SRow& g = grow[L.plan.recv_idx[t]];
           const int32_t len = rd.get1<int32_t>();
-          g.cols.resize((size_t)len);
-          g.vals.resize((size_t)len);
-          rd.get(g.cols.data(), (size_t)len);
-          rd.get(g.vals.data(), (size_t)len);
+          std::vector<std::pair<int32_t, double>> row((size_t)len);
+          for (int32_t e = 0; e < len; ++e)
+          {
+            const int o = rd.get1<int32_t>();
+            const int32_t id = rd.get1<int32_t>();
+            row[e] = {local_id(o, id), rd.get1<double>()};
+          }
+          std::sort(row.begin(), row.end(), [](const std::pair<int32_t, double>& x, const std::pair<int32_t, double>& y)
+                    { return x.first < y.first; });
+          for (auto& e : row)
+          {
+            g.cols.push_back(e.first);
+            g.vals.push_back(e.second);
+          }
         }
       }
     }
-    // provisional ghost aggregates, numbered in (owner, owner-local id) order
-    std::map<std::pair<int, int32_t>, int32_t> gmap;
-    for (int g = 0; g < L.n_ghost; ++g)
-      for (int32_t c : grow[g].cols)
-        gmap[{L.ghost_src[g], c}] = 0;
-    {
-      int32_t id = 0;
-      for (auto& kv : gmap)
-        kv.second = id++;
-    }
-    const int n_prov = (int)gmap.size();
+    // P over owned + ghost rows; A P for the owned rows; P^T (A P): rows < na are mine, the others are
+    // partial rows of the neighbours' aggregates and go to their owners
     Csr Pext;
     Pext.n_rows = n + L.n_ghost;
-    Pext.n_cols = na + n_prov;
     Pext.ptr = P.ptr;
     Pext.cols = P.cols;
     Pext.vals = P.vals;
     Pext.ptr.resize((size_t)n + L.n_ghost + 1);
     for (int g = 0; g < L.n_ghost; ++g)
     {
-      std::vector<std::pair<int32_t, double>> row;
-      for (size_t t = 0; t < grow[g].cols.size(); ++t)
-        row.emplace_back(na + gmap[{L.ghost_src[g], grow[g].cols[t]}], grow[g].vals[t]);
-      std::sort(row.begin(), row.end());
-      for (auto& e : row)
-      {
-        Pext.cols.push_back(e.first);
-        Pext.vals.push_back(e.second);
-      }
+      Pext.cols.insert(Pext.cols.end(), grow[g].cols.begin(), grow[g].cols.end());
+      Pext.vals.insert(Pext.vals.end(), grow[g].vals.begin(), grow[g].vals.end());
       Pext.ptr[(size_t)n + g + 1] = (int32_t)Pext.cols.size();
     }
+    Pext.n_cols = na + (int)gkeys.size();
+    P.n_cols = Pext.n_cols;
     Csr AP = spgemm(M, Pext);
-    Csr Ac = spgemm(transpose(P), AP); // Galerkin product: owned coarse rows, owned + ghost coarse columns
-    // keep only the ghost aggregates A_c references; the (owner, id) order survives, so the column
-    // renumbering is monotone and the rows stay sorted
-    std::vector<int32_t> remap((size_t)n_prov, -1);
-    for (int32_t c : Ac.cols)
+    Csr Call = spgemm(transpose(P), AP); // (na + ghosts) x (na + ghosts)
+    std::vector<std::map<int32_t, double>> crow((size_t)na); // my coarse rows, accumulated
+    for (int I = 0; I < na; ++I)
+      for (int32_t j = Call.ptr[I]; j < Call.ptr[I + 1]; ++j)
+        crow[I][Call.cols[j]] += Call.vals[j];
+    if (cm.nranks > 1)
+    {
+      std::map<int, std::vector<char>> out;
+      for (int I = na; I < Call.n_rows; ++I)
+      {
+        const int32_t len = Call.ptr[I + 1] - Call.ptr[I];
+        if (len == 0)
+          continue;
+        const Key ki = gkeys[(size_t)(I - na)];
+        std::vector<char>& b = out[ki.first];
+        put1<int32_t>(b, ki.second);
+        put1<int32_t>(b, len);
+        for (int32_t j = Call.ptr[I]; j < Call.ptr[I + 1]; ++j)
+        {
+          const Key kc = key_of(Call.cols[j]);
+          put1<int32_t>(b, kc.first);
+          put1<int32_t>(b, kc.second);
+          put1<double>(b, Call.vals[j]);
+        }
+      }
+      std::vector<int> dests;
+      std::vector<std::vector<char>> msgs;
+      for (auto& kv : out)
+      {
+        dests.push_back(kv.first);
+        msgs.push_back(std::move(kv.second));
+      }
+      for (auto& m : neighbor_exchange(cm, dests, msgs))
+      {
+        Reader rd{m.second.data(), m.second.data() + m.second.size()};
+        while (rd.p < rd.e)
+        {
+          const int32_t I = rd.get1<int32_t>();
+          const int32_t len = rd.get1<int32_t>();
+          PMGX_REQUIRE(I >= 0 && I < na, "amg_setup: partial coarse row %d of %d from rank %d", I, na, m.first);
+          for (int32_t e = 0; e < len; ++e)
+          {
+            const int o = rd.get1<int32_t>();
+            const int32_t id = rd.get1<int32_t>();
+            crow[I][local_id(o, id)] += rd.get1<double>();
+          }
+        }
+      }
+    }
+    // final coarse numbering: the ghost aggregates that A_c or P reference, sorted by (owner, id)
+    const int n_prov = (int)gkeys.size();
+    std::vector<char> used((size_t)n_prov, 0);
+    for (int I = 0; I < na; ++I)
+      for (auto& e : crow[I])
+        if (e.first >= na)
+          used[e.first - na] = 1;
+    for (int32_t c : P.cols)
       if (c >= na)
-        remap[c - na] = 0;
+        used[c - na] = 1;
+    std::vector<int32_t> order;
+    for (int g = 0; g < n_prov; ++g)
+      if (used[g])
+        order.push_back(g);
+    std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return gkeys[a] < gkeys[b]; });
+    std::vector<int32_t> remap((size_t)n_prov, -1);
     Level C;
     C.n_owned = na;
+    C.n_ghost = (int)order.size();
+    for (size_t t = 0; t < order.size(); ++t)
     {
-      int32_t id = 0;
-      for (auto& kv : gmap)
-        if (remap[kv.second] == 0)
-        {
-          remap[kv.second] = id++;
-          C.ghost_src.push_back(kv.first.first);
-          C.ghost_rid.push_back(kv.first.second);
-        }
-      C.n_ghost = id;
+      remap[order[t]] = (int32_t)t;
+      C.ghost_src.push_back(gkeys[order[t]].first);
+      C.ghost_rid.push_back(gkeys[order[t]].second);
     }
-    for (int32_t& c : Ac.cols)
-      if (c >= na)
-        c = na + remap[c - na];
-    Ac.n_cols = na + C.n_ghost;
-    C.A = std::move(Ac);
+    auto final_col = [&](int32_t c) -> int32_t { return c < na ? c : (remap[c - na] < 0 ? -1 : na + remap[c - na]); };
+    {
+      Csr& Ac = C.A;
+      Ac.n_rows = na;
+      Ac.n_cols = na + C.n_ghost;
+      Ac.ptr.assign((size_t)na + 1, 0);
+      std::vector<std::pair<int32_t, double>> row;
+      for (int I = 0; I < na; ++I)
+      {
+        row.clear();
+        for (auto& e : crow[I])
+          row.emplace_back(final_col(e.first), e.second);
+        std::sort(row.begin(), row.end(), [](const std::pair<int32_t, double>& x, const std::pair<int32_t, double>& y)
+                  { return x.first < y.first; });
+        for (auto& e : row)
+        {
+          Ac.cols.push_back(e.first);
+          Ac.vals.push_back(e.second);
+        }
+        Ac.ptr[I + 1] = (int32_t)Ac.cols.size();
+      }
+    }
+    // P and the restriction R = (P over owned + ghost rows, my aggregates only)^T in the final numbering
+    {
+      std::vector<std::pair<int32_t, double>> row;
+      for (int i = 0; i < n; ++i)
+      {
+        row.clear();
+        for (int32_t j = P.ptr[i]; j < P.ptr[i + 1]; ++j)
+          row.emplace_back(final_col(P.cols[j]), P.vals[j]);
+        std::sort(row.begin(), row.end(), [](const std::pair<int32_t, double>& x, const std::pair<int32_t, double>& y)
+                  { return x.first < y.first; });
+        for (int32_t j = P.ptr[i], t = 0; j < P.ptr[i + 1]; ++j, ++t)
+          P.cols[j] = row[t].first, P.vals[j] = row[t].second;
+      }
+      P.n_cols = na + C.n_ghost;
+      Csr Pmine; // rows: owned + ghost fine dofs, columns: my aggregates
+      Pmine.n_rows = n + L.n_ghost;
+      Pmine.n_cols = na;
+      Pmine.ptr.assign((size_t)Pmine.n_rows + 1, 0);
+      for (int i = 0; i < Pmine.n_rows; ++i)
+      {
+        for (int32_t j = Pext.ptr[i]; j < Pext.ptr[i + 1]; ++j)
+          if (Pext.cols[j] < na)
+          {
+            Pmine.cols.push_back(Pext.cols[j]);
+            Pmine.vals.push_back(Pext.vals[j]);
+          }
+        Pmine.ptr[i + 1] = (int32_t)Pmine.cols.size();
+      }
+      L.R = transpose(Pmine);
+    }
     // coarse halo plan: my ghosts are grouped by owner already; tell the owners what I need
     {
       Plan& cp = C.plan;
@@ -867,6 +978,7 @@ int pmgx_amg_level_dist_sizes(pmgx_amg_hier* h, int level, long long* out_h)
   out_h[5] = (long long)L.plan.recv_idx.size();
   out_h[6] = L.dense ? 1 : 0;
   out_h[7] = L.n_global;
+  out_h[8] = L.R.nnz();
   PMGX_API_END
 }
 
@@ -895,6 +1007,20 @@ int pmgx_amg_level_dist_get(pmgx_amg_hier* h, int level, int* ghost_src_h, int32
     std::copy(L.plan.recv_idx.begin(), L.plan.recv_idx.end(), recv_idx_h);
   if (inv_rows_h)
     std::copy(L.inv_rows.begin(), L.inv_rows.end(), inv_rows_h);
+  PMGX_API_END
+}
+
+int pmgx_amg_level_get_restriction(pmgx_amg_hier* h, int level, int32_t* r_ptr_h, int32_t* r_cols_h, double* r_vals_h)
+{
+  PMGX_API_BEGIN
+  PMGX_REQUIRE(h && level >= 0 && level < (int)h->H.levels.size(), "amg_level_get_restriction: bad arguments");
+  const Level& L = h->H.levels[level];
+  if (r_ptr_h && !L.R.ptr.empty())
+    std::copy(L.R.ptr.begin(), L.R.ptr.end(), r_ptr_h);
+  if (r_cols_h)
+    std::copy(L.R.cols.begin(), L.R.cols.end(), r_cols_h);
+  if (r_vals_h)
+    std::copy(L.R.vals.begin(), L.R.vals.end(), r_vals_h);
   PMGX_API_END
 }
 

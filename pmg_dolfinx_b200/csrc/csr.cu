@@ -85,6 +85,137 @@ k_spmv_ghost_rows(int n_list, const int32_t* __restrict__ rows, const double* __
     y[row] += s;
 }
 
+// ---- Chebyshev update fused into the SpMV (ChebEp, operator.hpp).  Same arithmetic, in the same order,
+// as the stand-alone passes k_cheb_init / k_cheb_step / k_cheb_last / k_cheb_step_xonly of solvers.cu.
+template <int MODE>
+__device__ __forceinline__ void cheb_row(int i, double q, const double* __restrict__ in, const ChebEp& e)
+{
+  if (MODE == ChebEp::INIT)
+  {
+    const double rv = q * (-1.0) + e.b[i];
+    e.r[i] = rv;
+    e.z_out[i] = (rv * e.dinv[i]) * e.c0;
+  }
+  else if (MODE == ChebEp::LAST)
+    e.r[i] = q * (-1.0) + e.r[i];
+  else
+  {
+    const double rv = q * (-1.0) + e.r[i];
+    const double zo = in[i];
+    const double zs = zo * e.c1;
+    const double zv = (rv * e.dinv[i]) * e.c2 + zs;
+    if (MODE == ChebEp::STEP)
+    {
+      e.r[i] = rv;
+      e.z_out[i] = zv;
+    }
+    const double xo = e.defer == 2 ? zo : (e.defer == 1 ? zo * 1.0 + e.x[i] : e.x[i]);
+    e.x[i] = zv * 1.0 + xo;
+  }
+}
+
+// owned-column block; rows that also hold ghost columns park their partial sum in e.scratch and are
+// finished by k_spmv_cheb_ghost_rows once the halo is in
+template <typename VT, bool D16, int MODE>
+__global__ void __launch_bounds__(ST)
+k_spmv_cheb(int n_rows, const VT* __restrict__ vals, const int32_t* __restrict__ beg, const int32_t* __restrict__ end,
+            const int32_t* __restrict__ row_ptr, const int16_t* __restrict__ dcol, const int32_t* __restrict__ cols,
+            const double* __restrict__ x, const ChebEp e)
+{
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = gt / LPR, lane = gt % LPR;
+  double s = 0.0;
+  if (row < n_rows)
+  {
+    const int en = end[row];
+    for (int j0 = beg[row] + lane; j0 < en; j0 += UNR * LPR)
+    {
+      int c[UNR];
+      VT v[UNR];
+#pragma unroll
+      for (int t = 0; t < UNR; ++t)
+      {
+        const int jj = j0 + t * LPR;
+        const bool ok = jj < en;
+        c[t] = ok ? (D16 ? row + (int)__ldcs(dcol + jj) : __ldcs(cols + jj)) : -1;
+        v[t] = ok ? __ldcs(vals + jj) : VT(0);
+      }
+#pragma unroll
+      for (int t = 0; t < UNR; ++t)
+        if (c[t] >= 0)
+          s = fma((double)v[t], x[c[t]], s);
+    }
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1)
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (row < n_rows && lane == 0)
+  {
+    if (end[row] < row_ptr[row + 1])
+      e.scratch[row] = s; // ghost columns to come
+    else
+      cheb_row<MODE>(row, s, x, e);
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(ST)
+k_spmv_cheb_ghost_rows(int n_list, const int32_t* __restrict__ rows, const double* __restrict__ vals,
+                       const int32_t* __restrict__ off_diag, const int32_t* __restrict__ row_ptr,
+                       const int32_t* __restrict__ cols, const double* __restrict__ x, const ChebEp e)
+{
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const int li = gt / LPR, lane = gt % LPR;
+  double s = 0.0;
+  int row = -1;
+  if (li < n_list)
+  {
+    row = rows[li];
+    const int en = row_ptr[row + 1];
+    for (int j = off_diag[row] + lane; j < en; j += LPR)
+      s = fma(vals[j], x[cols[j]], s);
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1)
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (row >= 0 && lane == 0)
+    cheb_row<MODE>(row, e.scratch[row] + s, x, e);
+}
+
+template <typename VT, bool D16>
+void launch_spmv_cheb(pmgx_ctx* c, int grid, int n_rows, const VT* vals, const int32_t* beg, const int32_t* end,
+                      const int32_t* row_ptr, const int16_t* dcol, const int32_t* cols, const double* x, const ChebEp& e)
+{
+  switch (e.mode)
+  {
+  case ChebEp::INIT: k_spmv_cheb<VT, D16, ChebEp::INIT><<<grid, ST, 0, c->stream>>>(n_rows, vals, beg, end, row_ptr, dcol, cols, x, e); break;
+  case ChebEp::STEP: k_spmv_cheb<VT, D16, ChebEp::STEP><<<grid, ST, 0, c->stream>>>(n_rows, vals, beg, end, row_ptr, dcol, cols, x, e); break;
+  case ChebEp::LAST: k_spmv_cheb<VT, D16, ChebEp::LAST><<<grid, ST, 0, c->stream>>>(n_rows, vals, beg, end, row_ptr, dcol, cols, x, e); break;
+  default: k_spmv_cheb<VT, D16, ChebEp::XONLY><<<grid, ST, 0, c->stream>>>(n_rows, vals, beg, end, row_ptr, dcol, cols, x, e); break;
+  }
+  check_launch("k_spmv_cheb");
+  count_launch(c);
+}
+
+void launch_ghost_rows_cheb(const CsrOperator* A, const double* x, const ChebEp& e)
+{
+  pmgx_ctx* c = A->ctx;
+  const int g2 = (int)(((long long)A->n_ghost_rows * LPR + ST - 1) / ST);
+#define PMGX_GR(M)                                                                                                     \
+  k_spmv_cheb_ghost_rows<M><<<g2, ST, 0, c->stream>>>(A->n_ghost_rows, A->ghost_rows.p, A->values.p, A->off_diag.p,    \
+                                                      A->row_ptr.p, A->cols.p, x, e)
+  switch (e.mode)
+  {
+  case ChebEp::INIT: PMGX_GR(ChebEp::INIT); break;
+  case ChebEp::STEP: PMGX_GR(ChebEp::STEP); break;
+  case ChebEp::LAST: PMGX_GR(ChebEp::LAST); break;
+  default: PMGX_GR(ChebEp::XONLY); break;
+  }
+#undef PMGX_GR
+  check_launch("k_spmv_cheb_ghost_rows");
+  count_launch(c);
+}
+
 __global__ void k_flag_ghost_rows(int n_rows, const int32_t* __restrict__ off_diag,
                                   const int32_t* __restrict__ row_ptr, int32_t* __restrict__ count,
                                   int32_t* __restrict__ list)
@@ -248,6 +379,47 @@ void CsrOperator::apply(double* x, double* y)
     check_launch("k_spmv_ghost_rows");
     count_launch(ctx);
   }
+}
+
+// fused apply + Chebyshev update: owned-column block (overlapping the halo) finishes the rows without
+// ghost columns, the interface rows are finished behind the exchange
+bool CsrOperator::apply_cheb(double* in, const ChebEp& e)
+{
+  cudaSetDevice(ctx->device);
+  PMGX_REQUIRE(n_ghost_rows == 0 || e.scratch, "apply_cheb: scratch vector missing");
+  const int grid = (int)(((long long)n_owned * LPR + ST - 1) / ST);
+  if (halo)
+    halo_fwd_begin(halo, in);
+  if (n_owned > 0)
+    launch_spmv_cheb<double, false>(ctx, grid, n_owned, values.p, row_ptr.p, off_diag.p, row_ptr.p, nullptr, cols.p, in, e);
+  if (halo)
+    halo_fwd_end(halo, in);
+  if (n_ghost_rows > 0)
+    launch_ghost_rows_cheb(this, in, e);
+  return true;
+}
+
+bool CsrOperatorLP::apply_cheb(double* in, const ChebEp& e)
+{
+  cudaSetDevice(ctx->device);
+  PMGX_REQUIRE(src->n_ghost_rows == 0 || e.scratch, "apply_cheb: scratch vector missing");
+  const int grid = (int)(((long long)n_owned * LPR + ST - 1) / ST);
+  if (halo)
+    halo_fwd_begin(halo, in);
+  if (n_owned > 0)
+  {
+    if (d16)
+      launch_spmv_cheb<float, true>(ctx, grid, n_owned, vals32.p, src->row_ptr.p, src->off_diag.p, src->row_ptr.p,
+                                    dcol16.p, nullptr, in, e);
+    else
+      launch_spmv_cheb<float, false>(ctx, grid, n_owned, vals32.p, src->row_ptr.p, src->off_diag.p, src->row_ptr.p,
+                                     nullptr, src->cols.p, in, e);
+  }
+  if (halo)
+    halo_fwd_end(halo, in);
+  if (src->n_ghost_rows > 0)
+    launch_ghost_rows_cheb(src, in, e);
+  return true;
 }
 
 void CsrOperatorLP::apply(double* x, double* y)

@@ -15,6 +15,8 @@ struct CsrOperator : pmgx_operator
   DevBuf<int32_t> ghost_rows; // rows with at least one ghost-column entry
   int n_ghost_rows = 0;
   void apply(double* x, double* y) override;
+  bool supports_cheb_fusion() const override { return true; }
+  bool apply_cheb(double* in, const ChebEp& e) override;
   void finish_setup(); // extracts diag^-1 (src/csr.hpp:101-112)
 };
 
@@ -30,6 +32,8 @@ struct CsrOperatorLP : pmgx_operator
   DevBuf<float> vals32;       // owned-column entries at their CSR positions
   DevBuf<int16_t> dcol16;     // col - row (d16) ...
   void apply(double* x, double* y) override;
+  bool supports_cheb_fusion() const override { return true; }
+  bool apply_cheb(double* in, const ChebEp& e) override;
 };
 CsrOperatorLP* make_lp(CsrOperator* A);
 } // namespace pmgx

@@ -38,6 +38,35 @@ void halo_setup_p2p(pmgx_halo* h);
 cudaStream_t halo_stream(pmgx_halo* h, pmgx_ctx* c);
 } // namespace pmgx
 
+namespace pmgx
+{
+// Chebyshev update fused into a ROW-COMPLETE operator apply (north_star item 2: "the Chebyshev recurrence
+// fuses axpy, Jacobi scaling and the residual update into the operator apply, so each smoothing step makes
+// one HBM pass").  q = A in is never stored: as soon as row i of it is complete the smoother's vector update
+// of entry i (src/chebyshev.hpp:56-68,73-83) is applied.  Possible for gather-type operators (CSR: a row is
+// owned by one lane group); the matrix-free operator scatter-adds into shared dofs, so its q is complete
+// only after the whole grid has finished and its update stays a separate pass (solvers.cu).
+struct ChebEp
+{
+  enum Mode
+  {
+    INIT = 0,  // in = x:  r = b - q ; z_out = c0 D^-1 r                                (:56-68)
+    STEP = 1,  // in = z:  r -= q ; z_out = c1 z + c2 D^-1 r ; x = z_out + (x [+ z])     (:76-83,73)
+    LAST = 2,  // in = z:  r -= q                                                        (:77)
+    XONLY = 3  // in = z:  x = (c1 z + c2 D^-1 (r - q)) + (x [+ z]); r and z are dead
+  };
+  int mode = INIT;
+  const double* b = nullptr;
+  double* r = nullptr;
+  double* z_out = nullptr;
+  double* x = nullptr;
+  const double* dinv = nullptr;
+  double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+  int defer = 0;          // the x += z of the previous pass was postponed to this one (1), and x was zero (2)
+  double* scratch = nullptr; // n_owned doubles: partial rows that wait for ghost columns
+};
+} // namespace pmgx
+
 // Operator concept of the reference (operator()(in,out) + get_diag_inverse,
 // src/chebyshev.hpp:53-56, src/cg.hpp:154-159) as a small polymorphic base.
 struct pmgx_operator
@@ -55,6 +84,14 @@ struct pmgx_operator
   virtual ~pmgx_operator() {}
   // y = A x (zero fill + halo update of x included)
   virtual void apply(double* x, double* y) = 0;
+  // fused apply + Chebyshev update (see ChebEp); false: not supported, the caller runs apply + a pass
+  virtual bool supports_cheb_fusion() const { return false; }
+  virtual bool apply_cheb(double* in, const pmgx::ChebEp& e)
+  {
+    (void)in;
+    (void)e;
+    return false;
+  }
 };
 
 struct pmgx_interp;

@@ -258,9 +258,72 @@ void check(const char* w) { check_launch(w); }
 namespace pmgx
 {
 
+// Row-complete operators (CSR): every iteration is ONE kernel -- the SpMV with the smoother's vector update
+// as its epilogue (ChebEp, operator.hpp; north_star item 2).  Same recurrence, same dead-work elimination as
+// below; z ping-pongs between two buffers because the SpMV gathers the old z while the new one is written.
+static void cheb_solve_fused(pmgx_cheb* s, pmgx_operator* A, double* x, const double* b, bool x_is_zero,
+                             ChebResidual final_r)
+{
+  pmgx_ctx* c = s->ctx;
+  const long long n = s->n_owned;
+  const double lmax = s->eig_max;
+  const size_t nt = (size_t)s->n_owned + s->n_ghost;
+  if (s->z2.n != nt)
+  {
+    s->z2.alloc(nt);
+    if (nt > 0)
+      PMGX_CUDA(cudaMemsetAsync(s->z2.p, 0, nt * sizeof(double), c->stream));
+  }
+  double* zin = s->z.p;
+  double* zout = s->z2.p;
+  ChebEp e;
+  e.b = b;
+  e.r = s->r.p;
+  e.x = x;
+  e.dinv = A->diag_inv.p;
+  e.scratch = s->q.p;
+  e.c0 = 4.0 / (3.0 * lmax);
+  if (x_is_zero)
+  {
+    k_cheb_init<false><<<fused_grid(c, n), FT, 0, c->stream>>>(b, nullptr, e.dinv, s->r.p, zin, x, e.c0, false, n,
+                                                              c->d_partials, c->d_counter, c->d_scalars + 8);
+    check("k_cheb_init");
+    count_launch(c);
+  }
+  else
+  {
+    e.mode = ChebEp::INIT;
+    e.z_out = zin;
+    A->apply_cheb(x, e);                                                           // :56-68
+  }
+  const int defer_mode = x_is_zero ? 2 : 1; // max_iter >= 2: the first x += z is always formed in the next pass
+  for (int i = 1; i <= s->max_iter; ++i)
+  {
+    const bool last = i == s->max_iter;
+    if (last && final_r == CHEB_R_NONE)
+      break;
+    if (last && final_r == CHEB_R_SPLIT)
+    {
+      A->apply(zin, s->q.p); // r = s->r - s->q, combined by the caller
+      break;
+    }
+    e.c1 = double(2 * i - 1) / double(2 * i + 3);
+    e.c2 = double(8 * i + 4) / double(2 * i + 3) / lmax;
+    e.defer = i == 1 ? defer_mode : 0;
+    e.mode = last ? ChebEp::LAST : ((i + 1 == s->max_iter && final_r == CHEB_R_NONE) ? ChebEp::XONLY : ChebEp::STEP);
+    e.z_out = zout;
+    A->apply_cheb(zin, e);                                                         // :76-83 (+ :73 of the next iteration)
+    if (e.mode == ChebEp::STEP)
+      std::swap(zin, zout);
+  }
+}
+
 void cheb_solve(pmgx_cheb* s, pmgx_operator* A, double* x, const double* b, double* hist, bool x_is_zero,
                 ChebResidual final_r)
 {
+  static const bool fuse = !(getenv("PMGX_CHEB_FUSE") && atoi(getenv("PMGX_CHEB_FUSE")) == 0);
+  if (fuse && !hist && s->max_iter >= 2 && A->supports_cheb_fusion())
+    return cheb_solve_fused(s, A, x, b, x_is_zero, final_r);
   pmgx_ctx* c = s->ctx;
   const long long n = s->n_owned;
   const double lmax = s->eig_max; // only the upper bound is used (chebyshev.hpp:51)

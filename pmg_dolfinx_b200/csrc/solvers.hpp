@@ -13,6 +13,7 @@ struct pmgx_cheb
   double eig_min = 0.0, eig_max = 1.0;
   int max_iter = 0;
   pmgx::DevBuf<double> z, q, r; // work vectors (owned + ghost), src/chebyshev.hpp:101-105
+  pmgx::DevBuf<double> z2;      // second z buffer of the fused (row-complete operator) path, allocated on first use
 };
 
 namespace pmgx

@@ -68,11 +68,11 @@ def _worker(rank, world, port, n, out):
                                     ctypes.cast(allgather, ctypes.c_void_p), None, 60, 10, ctypes.addressof(h)))
     levels = []
     for l in range(lib.pmgx_amg_num_levels(h)):
-        sz, ds = np.zeros(4, dtype=np.int64), np.zeros(8, dtype=np.int64)
+        sz, ds = np.zeros(4, dtype=np.int64), np.zeros(9, dtype=np.int64)
         check(lib.pmgx_amg_level_sizes(h, l, ptr(sz)))
         check(lib.pmgx_amg_level_dist_sizes(h, l, ptr(ds)))
         nrow, nnz, pc, pnnz = (int(v) for v in sz)
-        lo, lg, nsn, ns, nrn, nr, dense, nglob = (int(v) for v in ds)
+        lo, lg, nsn, ns, nrn, nr, dense, nglob, rnnz = (int(v) for v in ds)
         assert lo == nrow
         ap, ac, av = np.zeros(nrow + 1, np.int32), np.zeros(nnz, np.int32), np.zeros(nnz)
         pp, pcl, pv = np.zeros(nrow + 1, np.int32), np.zeros(pnnz, np.int32), np.zeros(pnnz)
@@ -85,7 +85,10 @@ def _worker(rank, world, port, n, out):
         inv = np.zeros(lo * nglob if dense else 0)
         check(lib.pmgx_amg_level_dist_get(h, l, ptr(gs), ptr(gr), ptr(psr), ptr(pso), ptr(psi), ptr(prr), ptr(pro),
                                           ptr(pri), ptr(inv) if dense else None))
-        levels.append(dict(n_owned=lo, n_ghost=lg, A=(ap, ac, av), P=(pp, pcl, pv, pc), lmax=lmax.value,
+        rp, rc, rv = np.zeros((pc + 1) if pc else 0, np.int32), np.zeros(rnnz, np.int32), np.zeros(rnnz)
+        if pc:
+            check(lib.pmgx_amg_level_get_restriction(h, l, ptr(rp), ptr(rc), ptr(rv)))
+        levels.append(dict(n_owned=lo, n_ghost=lg, A=(ap, ac, av), P=(pp, pcl, pv, pc), R=(rp, rc, rv), lmax=lmax.value,
                            ghost_src=gs, ghost_rid=gr, send=(psr, pso, psi), recv=(prr, pro, pri), dense=dense,
                            n_global=nglob, inv=inv))
     check(lib.pmgx_amg_destroy(h))
@@ -98,36 +101,49 @@ def _worker(rank, world, port, n, out):
     dist.destroy_process_group()
 
 
-def _assemble(per_rank, l):
-    """Global A_l, P_l (block diagonal) and row offsets of level l from the ranks' pieces."""
-    world = len(per_rank)
+def _gcols(per_rank, l):
+    """per rank: local column (owned + ghost) -> global id of level l, and the row offsets"""
     no = [r["levels"][l]["n_owned"] for r in per_rank]
     off = np.concatenate([[0], np.cumsum(no)])
+    out = []
+    for q, r in enumerate(per_rank):
+        L = r["levels"][l]
+        g = np.empty(no[q] + L["n_ghost"], dtype=np.int64)
+        g[: no[q]] = off[q] + np.arange(no[q])
+        if L["n_ghost"]:
+            g[no[q]:] = off[L["ghost_src"]] + L["ghost_rid"]
+        out.append(g)
+    return out, off, no
+
+
+def _assemble(per_rank, l):
+    """Global A_l, P_l, R_l and row offsets of level l from the ranks' pieces."""
+    gc, off, no = _gcols(per_rank, l)
     N = int(off[-1])
     Ar, Ac_, Av = [], [], []
     for q, r in enumerate(per_rank):
-        L = r["levels"][l]
-        ap, ac, av = L["A"]
-        gcol = np.empty(no[q] + L["n_ghost"], dtype=np.int64)
-        gcol[: no[q]] = off[q] + np.arange(no[q])
-        gcol[no[q]:] = off[L["ghost_src"]] + L["ghost_rid"] if L["n_ghost"] else []
+        ap, ac, av = r["levels"][l]["A"]
         Ar.append(off[q] + np.repeat(np.arange(no[q]), np.diff(ap)))
-        Ac_.append(gcol[ac])
+        Ac_.append(gc[q][ac])
         Av.append(av)
     A = sp.csr_matrix((np.concatenate(Av), (np.concatenate(Ar), np.concatenate(Ac_))), shape=(N, N))
-    P = None
-    if per_rank[0]["levels"][l]["P"][3] or any(r["levels"][l]["P"][3] for r in per_rank):
-        nc = [r["levels"][l + 1]["n_owned"] for r in per_rank]
-        coff = np.concatenate([[0], np.cumsum(nc)])
-        Pr, Pc, Pv = [], [], []
+    P = R = None
+    if any(r["levels"][l]["P"][3] for r in per_rank):
+        gcc, coff, nc = _gcols(per_rank, l + 1)
+        Pr, Pc, Pv, Rr, Rc, Rv = [], [], [], [], [], []
         for q, r in enumerate(per_rank):
             pp, pcl, pv, pc = r["levels"][l]["P"]
-            assert pc == nc[q]
+            assert pc == nc[q] + r["levels"][l + 1]["n_ghost"]     # P's columns: the next level's owned + ghost dofs
             Pr.append(off[q] + np.repeat(np.arange(no[q]), np.diff(pp)))
-            Pc.append(coff[q] + pcl)
+            Pc.append(gcc[q][pcl])
             Pv.append(pv)
+            rp, rc, rv = r["levels"][l]["R"]
+            Rr.append(coff[q] + np.repeat(np.arange(nc[q]), np.diff(rp[: nc[q] + 1])))
+            Rc.append(gc[q][rc])
+            Rv.append(rv)
         P = sp.csr_matrix((np.concatenate(Pv), (np.concatenate(Pr), np.concatenate(Pc))), shape=(N, int(coff[-1])))
-    return A, P, off
+        R = sp.csr_matrix((np.concatenate(Rv), (np.concatenate(Rr), np.concatenate(Rc))), shape=(int(coff[-1]), N))
+    return A, P, off, R
 
 
 @pytest.mark.parametrize("world", [2, 4])
@@ -142,12 +158,12 @@ def test_distributed_amg_setup_over_gloo(world, tmp_path):
     assert nl >= 2 and all(len(r["levels"]) == nl for r in per_rank)
     Ag, bcg = proto.p1_matrix(n[0])
     # level 0 in the gathered numbering is a permutation of the oracle matrix
-    A0, P0, off0 = _assemble(per_rank, 0)
+    A0, P0, off0, _ = _assemble(per_rank, 0)
     perm = np.concatenate([r["l2g"] for r in per_rank])
     assert abs(A0 - sp.csr_matrix(Ag)[perm][:, perm]).max() < 1e-14
     levels = []
     for l in range(nl):
-        A, P, off = _assemble(per_rank, l)
+        A, P, off, R = _assemble(per_rank, l)
         assert abs(A - A.T).max() <= 1e-12 * abs(A).max()
         lev = dict(A=A, dinv=1.0 / A.diagonal(), lmax=per_rank[0]["levels"][l]["lmax"])
         # every rank holds the same (global) eigenvalue estimate, an upper bound of the true one
@@ -157,8 +173,16 @@ def test_distributed_amg_setup_over_gloo(world, tmp_path):
         if P is not None:
             lev["P"] = P
             G = (P.T @ A @ P).tocsr()
-            An, _, _ = _assemble(per_rank, l + 1)
+            An, _, _, _ = _assemble(per_rank, l + 1)
             assert abs(G - An).max() <= 1e-11 * abs(G).max()                 # distributed Galerkin product
+            assert abs(R - P.T).max() <= 1e-15                               # R = the owned rows of the global P^T
+            # the prolongator is smoothed ACROSS the partition interfaces: it equals the one a single rank
+            # would build from the same aggregates, (I - omega D^-1 A) T with T = its unit-entry pattern
+            ranks_of_row = np.searchsorted(off, np.arange(A.shape[0]), side="right") - 1
+            coff = np.concatenate([[0], np.cumsum([r["levels"][l + 1]["n_owned"] for r in per_rank])])
+            ranks_of_col = np.searchsorted(coff, np.arange(P.shape[1]), side="right") - 1
+            Pc = P.tocoo()
+            assert (ranks_of_row[Pc.row] != ranks_of_col[Pc.col]).any()       # P does reach across ranks
             free = np.diff(A.indptr) > 1
             interior = np.abs(A @ np.ones(A.shape[0])) <= 1e-12 * A.diagonal()
             rs = np.asarray(P.sum(axis=1)).ravel()
@@ -182,7 +206,7 @@ def test_distributed_amg_setup_over_gloo(world, tmp_path):
     # coarsest level: the ranks' rows of the dense inverse
     last = [r["levels"][-1] for r in per_rank]
     assert all(L["dense"] for L in last)
-    Ac, _, off = _assemble(per_rank, nl - 1)
+    Ac, _, off, _ = _assemble(per_rank, nl - 1)
     N = Ac.shape[0]
     inv = np.zeros((N, N))
     for q, L in enumerate(last):
@@ -196,4 +220,10 @@ def test_distributed_amg_setup_over_gloo(world, tmp_path):
     b = np.random.default_rng(1).uniform(-1, 1, A0.shape[0]) * free0
     _, k_amg = proto.pcg(A0, b, lambda r: proto.vcycle(levels, 0, r), 1e-5, 100)
     _, k_jac = proto.pcg(A0, b, lambda r: levels[0]["dinv"] * r, 1e-5, 2000)
-    assert k_amg <= 9 and k_amg * 3 < k_jac, (k_amg, k_jac)
+    # ... and like a hierarchy that ignores the partition altogether (the single-rank set-up of the same matrix)
+    from test_amg_setup import _hierarchy
+    single = _hierarchy(Ag, min_coarse=60)
+    b_can = np.zeros_like(b)
+    b_can[perm] = b
+    _, k_single = proto.pcg(Ag, b_can, lambda r: proto.vcycle(single, 0, r), 1e-5, 100)
+    assert k_amg <= k_single + 1 and k_amg * 3 < k_jac, (k_amg, k_single, k_jac)
