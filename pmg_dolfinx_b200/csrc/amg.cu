@@ -260,6 +260,11 @@ int pmgx_coarse_create_amg(pmgx_ctx* ctx, pmgx_operator* A, int max_iter, double
   if (const char* e = getenv("PMGX_AMG_GAMMA"))
     M->gamma = atoi(e) == 2 ? 2 : 1;
   const bool use_lp = !(getenv("PMGX_AMG_LP") && atoi(getenv("PMGX_AMG_LP")) == 0);
+  // first level whose smoother runs the fused SpMV + Chebyshev kernels.  Measured at 1.59 M rows (coarse solve,
+  // 9 iterations): fused everywhere 7.56 ms, from level 1 on 7.08 ms, nowhere 7.25 ms -- on level 0 the
+  // epilogue's barrier shortens the streaming kernel's memory-level parallelism by more than the separate
+  // (L2-resident) vector pass costs; on the small levels the saved launches win.
+  const int fuse_from = getenv("PMGX_AMG_FUSE_FROM") ? atoi(getenv("PMGX_AMG_FUSE_FROM")) : 1;
   const int nl = (int)H.levels.size();
   M->lv.resize((size_t)nl);
   for (int l = 0; l < nl; ++l)
@@ -306,6 +311,7 @@ int pmgx_coarse_create_amg(pmgx_ctx* ctx, pmgx_operator* A, int max_iter, double
         return rc;
       // a coarsest level that could not be inverted densely is smoothed harder instead
       D.sm->max_iter = (last && !L.dense) ? 4 * nu : (l == 0 ? nu : nu_coarse);
+      D.sm->fuse = l >= fuse_from;
     }
     // level 0 is the only level that does not fit the L2: its smoother streams the matrix with FP32
     // values and 16-bit column deltas (PMGX_AMG_LP=0: the FP64 matrix)

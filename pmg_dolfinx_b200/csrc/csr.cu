@@ -149,12 +149,22 @@ k_spmv_cheb(int n_rows, const VT* __restrict__ vals, const int32_t* __restrict__
 #pragma unroll
   for (int o = LPR / 2; o > 0; o >>= 1)
     s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (row < n_rows && lane == 0)
+  // the vector update of the CTA's ST / LPR consecutive rows is done by ONE warp with coalesced accesses
+  // (lane 0 of every row group doing its own row wastes 7/8 of every sector and every issue slot)
+  __shared__ double sq[ST / LPR];
+  if (lane == 0)
+    sq[threadIdx.x / LPR] = s;
+  __syncthreads();
+  if (threadIdx.x < ST / LPR)
   {
-    if (end[row] < row_ptr[row + 1])
-      e.scratch[row] = s; // ghost columns to come
-    else
-      cheb_row<MODE>(row, s, x, e);
+    const int r = blockIdx.x * (ST / LPR) + threadIdx.x;
+    if (r < n_rows)
+    {
+      if (end[r] < row_ptr[r + 1])
+        e.scratch[r] = sq[threadIdx.x]; // ghost columns to come
+      else
+        cheb_row<MODE>(r, sq[threadIdx.x], x, e);
+    }
   }
 }
 

@@ -322,7 +322,7 @@ void cheb_solve(pmgx_cheb* s, pmgx_operator* A, double* x, const double* b, doub
                 ChebResidual final_r)
 {
   static const bool fuse = !(getenv("PMGX_CHEB_FUSE") && atoi(getenv("PMGX_CHEB_FUSE")) == 0);
-  if (fuse && !hist && s->max_iter >= 2 && A->supports_cheb_fusion())
+  if (fuse && s->fuse && !hist && s->max_iter >= 2 && A->supports_cheb_fusion())
     return cheb_solve_fused(s, A, x, b, x_is_zero, final_r);
   pmgx_ctx* c = s->ctx;
   const long long n = s->n_owned;

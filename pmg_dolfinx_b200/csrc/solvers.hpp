@@ -14,6 +14,7 @@ struct pmgx_cheb
   int max_iter = 0;
   pmgx::DevBuf<double> z, q, r; // work vectors (owned + ghost), src/chebyshev.hpp:101-105
   pmgx::DevBuf<double> z2;      // second z buffer of the fused (row-complete operator) path, allocated on first use
+  bool fuse = true;             // use the operator's fused apply + update when it has one
 };
 
 namespace pmgx

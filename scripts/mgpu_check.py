@@ -178,7 +178,8 @@ def run_check(api, ctx, rank, world, n=(9, 8, 7), perturb=0.15, log=print, gener
     # the coarse solver of the product: smoothed-aggregation PCG (distributed hierarchy; PMGX_CHECK_AMG=0:
     # Jacobi-PCG).  Both reach 1e-10, so the cycle's iterates equal the oracle's (Jacobi-CG to 1e-10)
     use_amg = os.environ.get("PMGX_CHECK_AMG", "1") != "0"
-    coarse = api.CoarseSolverType(ctx, A0, 60, 1e-10, amg=use_amg, min_coarse=40)
+    # (1e-12 in the M^-1 norm: the stage residuals below are compared to 1e-9 in the 2-norm)
+    coarse = api.CoarseSolverType(ctx, A0, 200 if not use_amg else 60, 1e-12, amg=use_amg, min_coarse=40)
     if rank == 0:
         log(f"[mgpu x{world}] coarse solver: {'SA-AMG PCG' if use_amg else 'Jacobi-PCG'}, levels on rank 0 "
             f"(rows, nnz, ghosts, dense): {coarse.levels()}")
@@ -209,7 +210,7 @@ def run_check(api, ctx, rank, world, n=(9, 8, 7), perturb=0.15, log=print, gener
         G0, _ = oo.geometry_factors(omesh.verts, omesh.geom_dofmap, degrees[0])
         A0o = oo.assemble_csr(degrees[0], O[0]["dm"], G0, np.full(omesh.ncells, 2.0), O[0]["bc"], O[0]["nd"])
         d0 = 1.0 / A0o.diagonal()
-        cso = lambda u0, b0: osol.cg(lambda v: A0o @ v, d0, u0, b0, 60, 1e-10)[0]
+        cso = lambda u0, b0: osol.cg(lambda v: A0o @ v, d0, u0, b0, 400, 1e-12)[0]
         Xo = om.dof_coords(omesh, degrees[-1])
         fo = 2.0 * np.pi ** 2 * 3 * np.sin(np.pi * Xo[:, 0]) * np.sin(np.pi * Xo[:, 1]) * np.sin(np.pi * Xo[:, 2]) + 1.0 + Xo[:, 0]
         bo = oo.rhs_collocated(omesh, degrees[-1], lambda _: fo, O[-1]["bc"])
@@ -221,7 +222,7 @@ def run_check(api, ctx, rank, world, n=(9, 8, 7), perturb=0.15, log=print, gener
         rn = pmg.apply(bvec, u, verbose=True)
         conv, crel = coarse.last_status()
         if rank == 0:
-            good = conv and coarse.last_iterations() <= (12 if use_amg else 60)
+            good = conv and coarse.last_iterations() <= (16 if use_amg else 200)
             ok = ok and good
             checks[f"V-cycle {it} coarse solve (iterations, converged, rel)"] = [coarse.last_iterations(), bool(conv), crel]
             log(f"[mgpu x{world}] V-cycle {it} coarse solve: {coarse.last_iterations()} iterations, "
