@@ -15,7 +15,8 @@ import torch  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "pmgx.h")
-LIBPATH = os.path.join(_HERE, "libpmgx.so")
+# PMGX_LIB: an alternative build of the same library (A/B builds of kernel compile-time parameters)
+LIBPATH = os.environ.get("PMGX_LIB") or os.path.join(_HERE, "libpmgx.so")
 
 _SCALARS = {
     "int": ctypes.c_int,

@@ -67,6 +67,9 @@ pmgx_halo* make_halo(pmgx_ctx* c, int n_owned, int n_ghost, const amg::Plan& p)
                                   p.recv_idx.data(), &h);
   if (rc != PMGX_OK)
     throw Error{rc};
+  // latency-bound exchanges: stay on the compute stream (PMGX_AMG_SINGLE_STREAM=0: dual-stream like level 0)
+  static const bool ss = !(getenv("PMGX_AMG_SINGLE_STREAM") && atoi(getenv("PMGX_AMG_SINGLE_STREAM")) == 0);
+  h->single_stream = ss && h->p2p && h->n_send() + h->n_recv() <= 65536;
   return h;
 }
 

@@ -249,59 +249,101 @@ __global__ void k_extract_diag_inv(int n_rows, const double* __restrict__ vals,
   dinv[i] = d;
 }
 
-// owned-column block with FP32 values and 16-bit column deltas (D16) or the FP64 matrix's 32-bit columns
+// ---- reduced-storage sliced-ELL twin (CsrOperatorLP, csr.hpp): thread per row, 32-row slices
+constexpr int SLICE = 32;
+
+// y[row] = sum_k val[slice_ptr[s] + k*32 + lane] * x[col]; the slice width is read once per warp
 template <bool D16>
 __global__ void __launch_bounds__(ST)
-k_spmv_lp(int n_rows, const float* __restrict__ vals, const int32_t* __restrict__ beg, const int32_t* __restrict__ end,
-          const int16_t* __restrict__ dcol, const int32_t* __restrict__ cols, const double* __restrict__ x,
-          double* __restrict__ y)
+k_spmv_sell(int n_rows, const long long* __restrict__ slice_ptr, const float* __restrict__ vals,
+            const int16_t* __restrict__ dcol, const int32_t* __restrict__ cols, const double* __restrict__ x,
+            double* __restrict__ y)
 {
-  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
-  const int row = gt / LPR, lane = gt % LPR;
-  double s = 0.0;
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = row >> 5, lane = row & 31;
+  if (s >= (n_rows + SLICE - 1) / SLICE)
+    return;
+  const long long b = slice_ptr[s];
+  const int w = (int)((slice_ptr[s + 1] - b) >> 5);
+  const float* v = vals + b + lane;
+  const int16_t* d = dcol + b + lane;
+  const int32_t* c = cols + b + lane;
+  const int r = row < n_rows ? row : n_rows - 1; // rows beyond the end only exist as padding of the last slice
+  double s0 = 0.0, s1 = 0.0;
+  int k = 0;
+  for (; k + 4 <= w; k += 4)
+  {
+    float vv[4];
+    int cc[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+    {
+      vv[t] = __ldcs(v + (k + t) * SLICE);
+      cc[t] = D16 ? r + (int)__ldcs(d + (k + t) * SLICE) : __ldcs(c + (k + t) * SLICE);
+    }
+    s0 = fma((double)vv[0], x[cc[0]], s0);
+    s1 = fma((double)vv[1], x[cc[1]], s1);
+    s0 = fma((double)vv[2], x[cc[2]], s0);
+    s1 = fma((double)vv[3], x[cc[3]], s1);
+  }
+  for (; k < w; ++k)
+  {
+    const float vv = __ldcs(v + k * SLICE);
+    const int cc = D16 ? r + (int)__ldcs(d + k * SLICE) : __ldcs(c + k * SLICE);
+    s0 = fma((double)vv, x[cc], s0);
+  }
+  if (row < n_rows)
+    y[row] = s0 + s1;
+}
+
+// widths[s] = 32 * max over the slice's rows of the owned-column length; overflow: a delta does not fit 16 bits
+__global__ void k_sell_widths(int n_rows, const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ off_diag,
+                              const int32_t* __restrict__ cols, long long* __restrict__ widths, int* __restrict__ overflow)
+{
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  int len = 0;
+  bool ovf = false;
   if (row < n_rows)
   {
-    const int e = end[row];
-    for (int j0 = beg[row] + lane; j0 < e; j0 += UNR * LPR)
+    len = off_diag[row] - row_ptr[row];
+    for (int j = row_ptr[row]; j < off_diag[row]; ++j)
     {
-      int c[UNR];
-      float v[UNR];
-#pragma unroll
-      for (int t = 0; t < UNR; ++t)
-      {
-        const int jj = j0 + t * LPR;
-        const bool ok = jj < e;
-        c[t] = ok ? (D16 ? row + (int)__ldcs(dcol + jj) : __ldcs(cols + jj)) : -1;
-        v[t] = ok ? __ldcs(vals + jj) : 0.f;
-      }
-#pragma unroll
-      for (int t = 0; t < UNR; ++t)
-        if (c[t] >= 0)
-          s = fma((double)v[t], x[c[t]], s);
+      const int dlt = cols[j] - row;
+      ovf = ovf || dlt > 32767 || dlt < -32767;
     }
   }
 #pragma unroll
-  for (int o = LPR / 2; o > 0; o >>= 1)
-    s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (row < n_rows && lane == 0)
-    y[row] = s;
+  for (int o = 16; o > 0; o >>= 1)
+    len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+  if (__any_sync(0xffffffffu, ovf) && (threadIdx.x & 31) == 0)
+    atomicOr(overflow, 1);
+  if ((threadIdx.x & 31) == 0 && row < n_rows)
+    widths[row >> 5] = (long long)len * SLICE;
 }
 
-__global__ void k_make_lp(int n_rows, const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ off_diag,
-                          const int32_t* __restrict__ cols, const double* __restrict__ vals, float* __restrict__ v32,
-                          int16_t* __restrict__ d16, int* __restrict__ overflow)
+__global__ void k_sell_fill(int n_rows, const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ off_diag,
+                            const int32_t* __restrict__ cols, const double* __restrict__ vals,
+                            const long long* __restrict__ slice_ptr, float* __restrict__ v32, int16_t* __restrict__ d16,
+                            int32_t* __restrict__ c32)
 {
-  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
-  const int row = gt / LPR, lane = gt % LPR;
-  if (row >= n_rows)
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = row >> 5, lane = row & 31;
+  if (s >= (n_rows + SLICE - 1) / SLICE)
     return;
-  for (int j = row_ptr[row] + lane; j < row_ptr[row + 1]; j += LPR)
+  const long long b = slice_ptr[s];
+  const int w = (int)((slice_ptr[s + 1] - b) >> 5);
+  const int r = row < n_rows ? row : n_rows - 1;
+  const int beg = row < n_rows ? row_ptr[row] : 0, len = row < n_rows ? off_diag[row] - row_ptr[row] : 0;
+  for (int k = 0; k < w; ++k)
   {
-    v32[j] = (float)vals[j];
-    const int d = cols[j] - row;
-    if (j < off_diag[row] && (d > 32767 || d < -32767))
-      atomicOr(overflow, 1);
-    d16[j] = (int16_t)d;
+    const long long p = b + (long long)k * SLICE + lane;
+    const bool ok = k < len;
+    v32[p] = ok ? (float)vals[beg + k] : 0.f;
+    const int col = ok ? cols[beg + k] : r;
+    if (d16)
+      d16[p] = (int16_t)(col - r);
+    if (c32)
+      c32[p] = col;
   }
 }
 
@@ -409,51 +451,28 @@ bool CsrOperator::apply_cheb(double* in, const ChebEp& e)
   return true;
 }
 
-bool CsrOperatorLP::apply_cheb(double* in, const ChebEp& e)
-{
-  cudaSetDevice(ctx->device);
-  PMGX_REQUIRE(src->n_ghost_rows == 0 || e.scratch, "apply_cheb: scratch vector missing");
-  const int grid = (int)(((long long)n_owned * LPR + ST - 1) / ST);
-  if (halo)
-    halo_fwd_begin(halo, in);
-  if (n_owned > 0)
-  {
-    if (d16)
-      launch_spmv_cheb<float, true>(ctx, grid, n_owned, vals32.p, src->row_ptr.p, src->off_diag.p, src->row_ptr.p,
-                                    dcol16.p, nullptr, in, e);
-    else
-      launch_spmv_cheb<float, false>(ctx, grid, n_owned, vals32.p, src->row_ptr.p, src->off_diag.p, src->row_ptr.p,
-                                     nullptr, src->cols.p, in, e);
-  }
-  if (halo)
-    halo_fwd_end(halo, in);
-  if (src->n_ghost_rows > 0)
-    launch_ghost_rows_cheb(src, in, e);
-  return true;
-}
-
 void CsrOperatorLP::apply(double* x, double* y)
 {
   cudaSetDevice(ctx->device);
-  const int grid = (int)(((long long)n_owned * LPR + ST - 1) / ST);
   if (n_ghost > 0)
     vec::set(ctx, y + n_owned, n_ghost, 0.0);
   if (halo)
     halo_fwd_begin(halo, x);
   if (n_owned > 0)
   {
+    const int grid = (n_slices * SLICE + ST - 1) / ST;
     if (d16)
-      k_spmv_lp<true><<<grid, ST, 0, ctx->stream>>>(n_owned, vals32.p, src->row_ptr.p, src->off_diag.p, dcol16.p, nullptr, x, y);
+      k_spmv_sell<true><<<grid, ST, 0, ctx->stream>>>(n_owned, slice_ptr.p, vals32.p, dcol16.p, nullptr, x, y);
     else
-      k_spmv_lp<false><<<grid, ST, 0, ctx->stream>>>(n_owned, vals32.p, src->row_ptr.p, src->off_diag.p, nullptr, src->cols.p, x, y);
-    check_launch("k_spmv_lp");
+      k_spmv_sell<false><<<grid, ST, 0, ctx->stream>>>(n_owned, slice_ptr.p, vals32.p, nullptr, cols32.p, x, y);
+    check_launch("k_spmv_sell");
     count_launch(ctx);
   }
   if (halo)
     halo_fwd_end(halo, x);
   if (src->n_ghost_rows > 0)
   {
-    // the (small) ghost-column block stays FP64
+    // the (small) ghost-column block stays FP64 CSR
     const int g2 = (int)(((long long)src->n_ghost_rows * LPR + ST - 1) / ST);
     k_spmv_ghost_rows<<<g2, ST, 0, ctx->stream>>>(src->n_ghost_rows, src->ghost_rows.p, src->values.p, src->off_diag.p,
                                                   src->row_ptr.p, src->cols.p, x, y);
@@ -475,24 +494,45 @@ CsrOperatorLP* make_lp(CsrOperator* A)
   L->diag_inv.alloc((size_t)A->n_owned);
   if (A->n_owned > 0)
     PMGX_CUDA(cudaMemcpyAsync(L->diag_inv.p, A->diag_inv.p, (size_t)A->n_owned * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-  const size_t nnz = (size_t)std::max<long long>(A->nnz, 1);
-  L->vals32.alloc(nnz);
-  L->dcol16.alloc(nnz);
+  const int n = A->n_owned;
+  L->n_slices = (n + SLICE - 1) / SLICE;
+  L->slice_ptr.alloc((size_t)L->n_slices + 1);
+  PMGX_CUDA(cudaMemsetAsync(L->slice_ptr.p, 0, ((size_t)L->n_slices + 1) * sizeof(long long), c->stream));
   DevBuf<int> ovf;
   ovf.alloc(1);
   PMGX_CUDA(cudaMemsetAsync(ovf.p, 0, sizeof(int), c->stream));
-  if (A->n_owned > 0)
+  long long total = 0;
+  if (n > 0)
   {
-    k_make_lp<<<(int)(((long long)A->n_owned * LPR + ST - 1) / ST), ST, 0, c->stream>>>(
-        A->n_owned, A->row_ptr.p, A->off_diag.p, A->cols.p, A->values.p, L->vals32.p, L->dcol16.p, ovf.p);
-    check_launch("k_make_lp");
+    // widths into slice_ptr[1..], then an inclusive prefix sum on the host (n_slices is ~50 k: set-up)
+    k_sell_widths<<<(n + ST - 1) / ST, ST, 0, c->stream>>>(n, A->row_ptr.p, A->off_diag.p, A->cols.p, L->slice_ptr.p + 1, ovf.p);
+    check_launch("k_sell_widths");
+    std::vector<long long> sp((size_t)L->n_slices + 1, 0);
+    PMGX_CUDA(cudaMemcpyAsync(sp.data(), L->slice_ptr.p, sp.size() * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    PMGX_CUDA(cudaStreamSynchronize(c->stream));
+    for (size_t i = 1; i < sp.size(); ++i)
+      sp[i] += sp[i - 1];
+    total = sp.back();
+    PMGX_CUDA(cudaMemcpyAsync(L->slice_ptr.p, sp.data(), sp.size() * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    PMGX_CUDA(cudaStreamSynchronize(c->stream));
   }
   int o = 0;
   PMGX_CUDA(cudaMemcpyAsync(&o, ovf.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   PMGX_CUDA(cudaStreamSynchronize(c->stream));
   L->d16 = o == 0;
-  if (!L->d16)
-    L->dcol16.release();
+  const size_t cap = (size_t)std::max<long long>(total, 1);
+  L->vals32.alloc(cap);
+  if (L->d16)
+    L->dcol16.alloc(cap);
+  else
+    L->cols32.alloc(cap);
+  if (n > 0)
+  {
+    k_sell_fill<<<(L->n_slices * SLICE + ST - 1) / ST, ST, 0, c->stream>>>(n, A->row_ptr.p, A->off_diag.p, A->cols.p, A->values.p,
+                                                                         L->slice_ptr.p, L->vals32.p, L->dcol16.p, L->cols32.p);
+    check_launch("k_sell_fill");
+    PMGX_CUDA(cudaStreamSynchronize(c->stream));
+  }
   return L.release();
 }
 

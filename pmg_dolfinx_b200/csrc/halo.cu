@@ -94,6 +94,23 @@ __global__ void k_wait_p2p(int n_nbr, const unsigned long long* __restrict__ fla
     wait_epoch(flags + t, epoch, timeout_ns); // bounded in wall time, see reduce.cuh
 }
 
+// wait + unpack in one kernel for SMALL exchanges on the compute stream (single_stream halos): every CTA
+// waits for the sources' flags itself, then unpacks its part
+__global__ void __launch_bounds__(PT)
+k_wait_unpack_p2p(int n_nbr, const unsigned long long* __restrict__ flags, const unsigned long long* __restrict__ epoch_ptr,
+                  unsigned long long timeout_ns, int n, const int32_t* __restrict__ idx, const double* __restrict__ bufs,
+                  double* __restrict__ out)
+{
+  const unsigned long long epoch = *epoch_ptr;
+  for (int s = threadIdx.x; s < n_nbr; s += blockDim.x)
+    wait_epoch(flags + s, epoch, timeout_ns);
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const double* in = bufs + (epoch & 1ull) * (size_t)n;
+  if (i < n)
+    out[idx[i]] = __ldcg(in + i);
+}
+
 __global__ void k_unpack_cg(int n, const int32_t* __restrict__ idx, const double* __restrict__ bufs,
                             const unsigned long long* __restrict__ epoch_ptr, double* __restrict__ out)
 {
@@ -117,16 +134,24 @@ static void halo_fwd_begin_p2p(pmgx_halo* h, double* x, const double* sub)
 {
   pmgx_ctx* c = h->ctx;
   const int ns = h->n_send(), nr = h->n_recv();
+  // single_stream (small exchanges of the AMG levels): everything on the compute stream, no event hops --
+  // the pack goes out here, the caller's owned-column work follows it, wait + unpack run in halo_fwd_end
+  cudaStream_t cst = h->single_stream ? c->stream : c->comm_stream;
   // a neighbour with an EMPTY segment still takes part in the flag handshake (the coarse levels of
   // the AMG hierarchy pair every send with a receive, amg_setup.cpp): the pack kernel runs whenever
   // there is a destination, the wait whenever there is a source
   if (!h->send_ranks.empty())
   {
-    k_pack_p2p<<<std::max((ns + PT - 1) / PT, 1), PT, 0, c->comm_stream>>>(ns, (int)h->send_ranks.size(), h->d_send_offsets.p,
+    k_pack_p2p<<<std::max((ns + PT - 1) / PT, 1), PT, 0, cst>>>(ns, (int)h->send_ranks.size(), h->d_send_offsets.p,
                                                              h->send_idx.p, x, sub, h->d_peer_dst.p, h->d_peer_stride.p,
                                                              h->d_peer_flag.p, h->d_epoch.p, h->d_ticket.p);
     check_launch("k_pack_p2p");
     count_launch(c);
+  }
+  if (h->single_stream)
+  {
+    h->pending_x = x;
+    return;
   }
   if (!h->recv_ranks.empty())
   {
@@ -151,6 +176,11 @@ void halo_fwd_begin(pmgx_halo* h, double* x, const double* sub)
     return;
   if (!h->p2p && ns == 0 && nr == 0)
     return; // NCCL path: empty segments are skipped on both sides
+  if (h->p2p && h->single_stream)
+  {
+    halo_fwd_begin_p2p(h, x, sub);
+    return;
+  }
   PMGX_CUDA(cudaEventRecord(h->ev_ready, c->stream));
   PMGX_CUDA(cudaStreamWaitEvent(c->comm_stream, h->ev_ready, 0));
   if (h->p2p)
@@ -193,6 +223,22 @@ void halo_fwd_begin(pmgx_halo* h, double* x, const double* sub)
 void halo_fwd_end(pmgx_halo* h, double* x)
 {
   (void)x;
+  if (h->pending_x)
+  {
+    // single-stream exchange: wait for the sources and unpack, right here on the compute stream
+    pmgx_ctx* c = h->ctx;
+    const int nr = h->n_recv();
+    if (!h->recv_ranks.empty())
+    {
+      const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(h->xbuf + 2 * (size_t)std::max(nr, 1));
+      k_wait_unpack_p2p<<<std::max((nr + PT - 1) / PT, 1), PT, 0, c->stream>>>(
+          (int)h->recv_ranks.size(), flags, h->d_epoch.p, c->p2p_timeout_ns, nr, h->recv_idx.p, h->xbuf, h->pending_x + h->n_owned);
+      check_launch("k_wait_unpack_p2p");
+      count_launch(c);
+    }
+    h->pending_x = nullptr;
+    return;
+  }
   if (!h->in_flight)
     return;
   // everything enqueued on the comm stream so far -- the exchange and any boundary-cell work the

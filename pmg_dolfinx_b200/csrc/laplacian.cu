@@ -1185,7 +1185,10 @@ struct AffCfg
   static constexpr size_t off_sf = off_su + (size_t)buf_doubles * sizeof(double);
   static constexpr size_t off_bar = off_sf + (size_t)buf_doubles * sizeof(double);
   static constexpr size_t smem = off_bar + 2 * sizeof(uint64_t);
-  static constexpr int minb = P <= 2 ? 6 : (TPB <= 64 ? 4 : 2);
+#ifndef PMGX_AFF_MINB_P4
+#define PMGX_AFF_MINB_P4 4
+#endif
+  static constexpr int minb = P <= 2 ? 6 : (TPB <= 64 ? (P == 4 ? PMGX_AFF_MINB_P4 : 4) : 2);
 };
 
 template <int P, int TPB>
@@ -1607,13 +1610,310 @@ void launch_apply_affine_t(pmgx_ctx* c, cudaStream_t st, const double* x, double
   }
 }
 
+
+// ---------------------------------------- the re-slabbed affine-geometry apply kernel --
+// Same thread mapping as k_apply_affine (thread t of a cell holds the (ix,iy) slab at iz = t in
+// registers, x and y contractions are register FMAs), but the z direction no longer re-reads every
+// z-row of the element n times as a broadcast (2 n^3 + 2 n^2 shared-memory doubles per thread; ncu:
+// L1/shared data pipe 78 % busy at 42 % FP64, profiles/r1_apply_p4_affine.txt).  Instead the data is
+// RE-SLABBED: every value crosses shared memory once per phase, written by the thread that owns it
+// and read by the thread that needs it --
+//   1. u(i,j,t)        -> thread j reads the slab u(i,j,.) and forms gz(i,j,l) = sum_m D[l][m] u(i,j,m)
+//   2. gz(i,j,l)       -> thread l reads gz(.,.,l): all three gradients at its points; G-transform;
+//                         x and y transposed contractions into the register accumulator
+//   3. fz(i,j,t)       -> thread j reads fz(i,j,.) and forms az(i,j,l) = sum_q D[q][l] fz(i,j,q)
+//   4. az(i,j,l)       -> thread l adds az(.,.,l) to its accumulator
+// 8 n^2 doubles per thread instead of 2 n^3 + 2 n^2 (P4: 200 vs 300; P6: 392 vs 784), four barriers
+// per batch instead of n + 1, and no broadcast reads.  Strides: slab stride SS = 1 (mod 16) and cell
+// stride CS = n (mod 16) doubles make the 8-byte bank of BOTH access patterns (unit stride in t when
+// writing, stride SS in t when reading) equal to lane + const: every 64-bit access is conflict-free.
+template <int P, int TPB, bool WL>
+struct Aff2Cfg
+{
+  static constexpr int n = P + 1;
+  static constexpr int n2 = n * n;
+  static constexpr int tpb = TPB;
+  // WL (warp-local): a warp holds 32 / n WHOLE cells (the lanes beyond that idle), so every exchange stays
+  // inside a warp and the phases are separated by __syncwarp() instead of CTA barriers: the warps of a CTA
+  // run free of each other (with 8-10 warps per SM a CTA barrier per phase leaves the schedulers empty)
+  static constexpr int cpw = 32 / n;
+  static constexpr int cpb = WL ? (TPB / 32) * cpw : TPB / n;
+  static constexpr int SE = (cpb * n + 3) & ~3;
+  static constexpr int ss = ((n2 - 1 + 15) / 16) * 16 + 1;                 // >= n2, = 1 mod 16
+  static constexpr int cs = ((n * ss - n + 15) / 16) * 16 + n;             // >= n * ss, = n mod 16
+  static constexpr uint32_t enc_bytes = n2 * SE * sizeof(int32_t);
+  static constexpr int buf_doubles = cpb * cs;
+  static constexpr size_t off_a = 2 * (size_t)enc_bytes;
+  static constexpr size_t off_b = off_a + (size_t)buf_doubles * sizeof(double);
+  static constexpr size_t off_bar = off_b + (size_t)buf_doubles * sizeof(double);
+  static constexpr size_t smem = off_bar + 2 * sizeof(uint64_t);
+  static constexpr int minb = P <= 2 ? 6 : (P == 4 && TPB <= 64 ? PMGX_AFF_MINB_P4 : (P <= 4 ? 4 : 2));
+};
+
+template <int P, int TPB, bool WL>
+__global__ void __launch_bounds__(TPB, Aff2Cfg<P, TPB, WL>::minb)
+k_apply_affine2(const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ Gc,
+                const int32_t* __restrict__ enc, const int32_t* __restrict__ perm,
+                const double* __restrict__ kappa, long long batch0, int cell0, int count, int nbatch)
+{
+  using C = Aff2Cfg<P, TPB, WL>;
+  constexpr int n = C::n, n2 = C::n2, CPB = C::cpb, SE = C::SE, SS = C::ss, CS = C::cs;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int32_t* sE = reinterpret_cast<const int32_t*>(smraw);
+  double* sA = reinterpret_cast<double*>(smraw + C::off_a);
+  double* sB = reinterpret_cast<double*>(smraw + C::off_b);
+  uint64_t* fullE = reinterpret_cast<uint64_t*>(smraw + C::off_bar);
+
+  const int tid = threadIdx.x;
+  int cl, t;
+  bool in_block;
+  if (WL)
+  {
+    const int warp = tid >> 5, lane = tid & 31;
+    const int cw = lane / n;
+    in_block = cw < C::cpw;
+    cl = warp * C::cpw + (in_block ? cw : 0);
+    t = in_block ? lane - cw * n : 0;
+  }
+  else
+  {
+    cl = tid / n;
+    t = tid - cl * n;
+    in_block = cl < CPB;
+  }
+  const int cls = in_block ? cl : 0;
+  const int slot = WL ? cls * n + t : tid;
+  const int my_nb = ((int)blockIdx.x < nbatch) ? (nbatch - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  auto phase_sync = [&]()
+  {
+    if (WL)
+      __syncwarp();
+    else
+      __syncthreads();
+  };
+
+  uint64_t pol = 0;
+  if (tid == 0)
+  {
+    mbar_init(&fullE[0], 1);
+    mbar_init(&fullE[1], 1);
+    mbar_fence_init();
+    pol = policy_evict_first();
+  }
+  __syncthreads();
+  auto issue_enc = [&](int it)
+  {
+    const long long gb = batch0 + blockIdx.x + (long long)it * gridDim.x;
+    mbar_expect_tx(&fullE[it & 1], C::enc_bytes);
+    bulk_g2s(const_cast<int32_t*>(sE) + (it & 1) * (n2 * SE), enc + gb * (long long)(n2 * SE), C::enc_bytes,
+             &fullE[it & 1], pol);
+  };
+  if (tid == 0 && my_nb > 0)
+    issue_enc(0);
+
+  const double wt = c_wts[P][t];
+  // writer view: element (slab s, row r) of this thread's z-index; reader view: this thread's slab
+  double* const wA = sA + cls * CS + t;
+  double* const wB = sB + cls * CS + t;
+  const double* const rA = sA + cls * CS + t * SS;
+  const double* const rB = sB + cls * CS + t * SS;
+
+  for (int it = 0; it < my_nb; ++it)
+  {
+    const int b = blockIdx.x + it * gridDim.x;
+    const int pl = b * CPB + cl;
+    const bool active = in_block && pl < count;
+
+    if (WL)
+    {
+      // the only CTA barrier of a batch: every warp is done with the dofmap buffer the next load will overwrite
+      __syncthreads();
+      if (tid == 0 && it + 1 < my_nb)
+        issue_enc(it + 1);
+    }
+    mbar_wait(&fullE[it & 1], (it >> 1) & 1);
+    const int32_t* dE = sE + (it & 1) * (n2 * SE) + slot;
+    double u[n2];
+    double g[6];
+    if (active)
+    {
+      const double kw = kappa[perm[cell0 + pl]] * wt; // kappa re-read on every apply (src/laplacian.hpp:230)
+      const double* gp = Gc + (size_t)(cell0 + pl) * 6;
+#pragma unroll
+      for (int c = 0; c < 6; ++c)
+        g[c] = gp[c] * kw;
+#pragma unroll
+      for (int a = 0; a < n2; ++a)
+      {
+        const int da = dE[a * SE];
+        const int idx = da < 0 ? ~da : da;
+        const double xv = x[idx];
+        if (da < 0)
+          y[idx] = xv; // Dirichlet row: y = x (src/laplacian.hpp:273-274)
+        u[a] = da < 0 ? 0.0 : xv;
+      }
+    }
+    else
+    {
+#pragma unroll
+      for (int c = 0; c < 6; ++c)
+        g[c] = 0.0;
+#pragma unroll
+      for (int a = 0; a < n2; ++a)
+        u[a] = 0.0;
+    }
+    // phase 1: u(i,j,t) -> A[slab j][i][t]
+    if (in_block)
+    {
+#pragma unroll
+      for (int i = 0; i < n; ++i)
+#pragma unroll
+        for (int j = 0; j < n; ++j)
+          wA[j * SS + i * n] = u[i * n + j];
+    }
+    phase_sync(); // (CTA-wide variant: every thread is also past the previous batch's reads of B and of the other dofmap buffer)
+    if (!WL && tid == 0 && it + 1 < my_nb)
+      issue_enc(it + 1);
+    // phase 2: slab j = t: gz(i,t,l) = sum_m D[l][m] u(i,t,m) -> B[slab l][i][t]
+#pragma unroll
+    for (int i = 0; i < n; ++i)
+    {
+      double v[n];
+#pragma unroll
+      for (int m = 0; m < n; ++m)
+        v[m] = rA[i * n + m];
+#pragma unroll
+      for (int l = 0; l < n; ++l)
+      {
+        double s = 0.0;
+#pragma unroll
+        for (int m = 0; m < n; ++m)
+          s = fma(c_D[P][l * n + m], v[m], s);
+        if (in_block)
+          wB[l * SS + i * n] = s;
+      }
+    }
+    phase_sync();
+    // phase 3: all three gradients at the points (i,j,t); transform; x / y transposed contractions;
+    // fz(i,j,t) -> A[slab j][i][t]
+    double acc[n2];
+#pragma unroll
+    for (int a = 0; a < n2; ++a)
+      acc[a] = 0.0;
+#pragma unroll
+    for (int i = 0; i < n; ++i)
+#pragma unroll
+      for (int j = 0; j < n; ++j)
+      {
+        double gx = 0.0, gy = 0.0;
+        const double gz = rB[i * n + j];
+#pragma unroll
+        for (int l = 0; l < n; ++l)
+        {
+          gx = fma(c_D[P][i * n + l], u[l * n + j], gx);
+          gy = fma(c_D[P][j * n + l], u[i * n + l], gy);
+        }
+        const double wij = c_wts[P][i] * c_wts[P][j]; // G(q) = w_i w_j w_k Gc
+        const double fx = wij * (g[0] * gx + g[1] * gy + g[2] * gz);
+        const double fy = wij * (g[1] * gx + g[3] * gy + g[4] * gz);
+        const double fz = wij * (g[2] * gx + g[4] * gy + g[5] * gz);
+#pragma unroll
+        for (int l = 0; l < n; ++l)
+        {
+          acc[l * n + j] = fma(c_D[P][i * n + l], fx, acc[l * n + j]);
+          acc[i * n + l] = fma(c_D[P][j * n + l], fy, acc[i * n + l]);
+        }
+        if (in_block)
+          wA[j * SS + i * n] = fz;
+      }
+    phase_sync();
+    // phase 4: slab j = t: az(i,t,l) = sum_q D[q][l] fz(i,t,q) -> B[slab l][i][t]
+#pragma unroll
+    for (int i = 0; i < n; ++i)
+    {
+      double v[n];
+#pragma unroll
+      for (int q = 0; q < n; ++q)
+        v[q] = rA[i * n + q];
+#pragma unroll
+      for (int l = 0; l < n; ++l)
+      {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < n; ++q)
+          s = fma(c_D[P][q * n + l], v[q], s);
+        if (in_block)
+          wB[l * SS + i * n] = s;
+      }
+    }
+    phase_sync();
+    // phase 5: acc(i,j,t) += az(i,j,t); scatter
+    if (active)
+    {
+#pragma unroll
+      for (int a = 0; a < n2; ++a)
+      {
+        const int da = dE[a * SE];
+        if (da >= 0)
+          atomicAdd(&y[da], acc[a] + rB[a]);
+      }
+    }
+    if (WL)
+      __syncwarp(); // B is rewritten in the next batch's phase 2 only after this warp's reads above
+  }
+}
+
+template <int P, int TPB, bool WL>
+void launch_apply_affine2_t(pmgx_ctx* c, cudaStream_t st, const double* x, double* y, const double* Gc,
+                            const int32_t* enc, const int32_t* perm, const double* kappa, long long batch0, int cell0,
+                            int count)
+{
+  using C = Aff2Cfg<P, TPB, WL>;
+  const bool timed = c->profiling && cell0 == 0; // per-kernel timing covers the interior-cell launch only
+  static int ctas_per_sm[64] = {0};
+  if (ctas_per_sm[c->device] == 0)
+  {
+    PMGX_CUDA(cudaFuncSetAttribute(k_apply_affine2<P, TPB, WL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem));
+    int nb = 0;
+    PMGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_apply_affine2<P, TPB, WL>, TPB, C::smem));
+    PMGX_REQUIRE(nb >= 1, "k_apply_affine2<%d,%d> does not fit on an SM", P, TPB);
+    ctas_per_sm[c->device] = nb;
+  }
+  const int nbatch = (count + C::cpb - 1) / C::cpb;
+  const int grid = std::min(nbatch, ctas_per_sm[c->device] * c->num_sms);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (timed)
+  {
+    PMGX_CUDA(cudaEventCreate(&e0));
+    PMGX_CUDA(cudaEventCreate(&e1));
+    PMGX_CUDA(cudaEventRecord(e0, st));
+  }
+  k_apply_affine2<P, TPB, WL><<<grid, TPB, C::smem, st>>>(x, y, Gc, enc, perm, kappa, batch0, cell0, count, nbatch);
+  check_launch("k_apply_affine2");
+  count_launch(c);
+  if (timed)
+  {
+    PMGX_CUDA(cudaEventRecord(e1, st));
+    c->prof[P].emplace_back(e0, e1);
+  }
+}
+
 template <int P>
 void launch_apply_affine(pmgx_ctx* c, cudaStream_t st, bool shfl, int tpb, const double* x, double* y,
                          const double* Gc, const int32_t* enc, const int32_t* perm, const double* kappa,
-                         long long batch0, int cell0, int count)
+                         long long batch0, int cell0, int count, int reslab = 0)
 {
   if (count <= 0)
     return;
+  // reslab: 1 = CTA-wide phases (batch layout of k_apply_affine), 2 = warp-local phases (batch layout of the shuffle kernel)
+  if (reslab == 2 && tpb == 64)
+    return launch_apply_affine2_t<P, 64, true>(c, st, x, y, Gc, enc, perm, kappa, batch0, cell0, count);
+  if (reslab == 2)
+    return launch_apply_affine2_t<P, 128, true>(c, st, x, y, Gc, enc, perm, kappa, batch0, cell0, count);
+  if (reslab && tpb == 64)
+    return launch_apply_affine2_t<P, 64, false>(c, st, x, y, Gc, enc, perm, kappa, batch0, cell0, count);
+  if (reslab)
+    return launch_apply_affine2_t<P, 128, false>(c, st, x, y, Gc, enc, perm, kappa, batch0, cell0, count);
   if (shfl && tpb == 64)
     return launch_apply_affine_shfl_t<P, 64>(c, st, x, y, Gc, enc, perm, kappa, batch0, cell0, count);
   if (shfl)
@@ -1629,7 +1929,7 @@ inline int tma_default_tpb(int P) { return (P == 1 || P >= 5) ? 64 : 128; }
 inline int tma_default_r(int P) { return 2; }
 // affine kernel (no geometry ring, so more small CTAs fit): measured at 100 M dofs, P1 3.45 vs 4.07 ms
 // (128 vs 64 threads), P2 1.67 vs 1.79, P3 1.61 vs 1.54, P4 1.34 vs 1.28, P5 1.20 vs 1.19, P6 2.06 vs 2.03
-inline int affine_default_tpb(int P) { return P <= 2 ? 128 : 64; }
+inline int affine_default_tpb(int P) { return P <= 2 ? 128 : 64; } // (P3 re-slab kernel: 1.201 / 1.202 ms at 64 / 128)
 
 template <int P>
 void launch_apply_tma(pmgx_ctx* c, cudaStream_t st, int tpb, int r, const double* x, double* y, const double* G,
@@ -1701,6 +2001,7 @@ struct Laplacian : pmgx_operator
   DevBuf<double> Gc;   // [n_list][6] per-cell geometry factor of affine cells
   bool affine = false; // every cell affine: k_apply_affine replaces the streamed-G kernels
   bool aff_shfl = false; // z contractions by warp shuffles instead of shared-memory rows (default for P <= 2)
+  int aff_reslab = 0; // re-slabbed z direction (k_apply_affine2): 1 CTA-wide phases, 2 warp-local phases
 
   int n_list() const { return n_l + n_b; }
 
@@ -1730,9 +2031,9 @@ struct Laplacian : pmgx_operator
     {
       if (lay.mode == 1 && affine)
       {
-        launch_apply_affine<PP>(ctx, cs, aff_shfl, tma_tpb, x, y, Gc.p, enc.p, perm.p, kappa, 0, 0, n_l);
+        launch_apply_affine<PP>(ctx, cs, aff_shfl, tma_tpb, x, y, Gc.p, enc.p, perm.p, kappa, 0, 0, n_l, aff_reslab);
         join_before_boundary();
-        launch_apply_affine<PP>(ctx, bs, aff_shfl, tma_tpb, x, y, Gc.p, enc.p, perm.p, kappa, lay.nb_l, n_l, n_b);
+        launch_apply_affine<PP>(ctx, bs, aff_shfl, tma_tpb, x, y, Gc.p, enc.p, perm.p, kappa, lay.nb_l, n_l, n_b, aff_reslab);
         done = true;
       }
       else if (lay.mode == 1 && use_tma)
@@ -1879,7 +2180,17 @@ int pmgx_laplacian_create(pmgx_ctx* ctx, int degree, int n_cells, const int32_t*
   L->aff_shfl = degree == 2;
   if (const char* e = getenv("PMGX_AFFINE_SHFL"))
     L->aff_shfl = atoi(e) != 0;
-  lay.cpb = (L->affine && L->aff_shfl) ? (L->tma_tpb / 32) * (32 / n) : L->tma_tpb / n;
+  // re-slabbed z direction (k_apply_affine2, warp-local phases): measured at 100 M dofs against the broadcast-row
+  // kernel -- P1 4.16 vs 3.44 ms, P2 1.76 vs 1.58, P3 1.20 vs 1.54, P4 1.41 vs 1.28, P5 2.40 vs 1.19, P6 3.09 vs 2.03:
+  // it halves the shared-memory wavefronts (ncu: L1/shared pipe 78 -> 53 %) but both kernels sit at 2 warps per
+  // scheduler with fixed-latency (DFMA dependency) stalls on top, so it only wins where its register count drops
+  // far enough to matter (P3)
+  L->aff_reslab = degree == 3 ? 2 : 0;
+  if (const char* e = getenv("PMGX_AFFINE_RESLAB"))
+    L->aff_reslab = atoi(e);
+  if (L->aff_reslab)
+    L->aff_shfl = false;
+  lay.cpb = (L->affine && (L->aff_shfl || L->aff_reslab == 2)) ? (L->tma_tpb / 32) * (32 / n) : L->tma_tpb / n;
   lay.S = (lay.cpb * n + 1) & ~1;
   lay.SE = (lay.cpb * n + 3) & ~3;
   lay.nb_l = (n_lcells + lay.cpb - 1) / lay.cpb;
@@ -1957,7 +2268,8 @@ int pmgx_laplacian_kernel_name(pmgx_operator* op, char* name_h, int cap)
   PMGX_REQUIRE(op && op->kind == pmgx_operator::LAPLACIAN && name_h && cap > 0, "laplacian_kernel_name: bad arguments");
   auto* L = static_cast<Laplacian*>(op);
   if (L->lay.mode == 1 && L->affine)
-    snprintf(name_h, cap, "%s<%d,%d>", L->aff_shfl ? "k_apply_affine_shfl" : "k_apply_affine", L->P, L->tma_tpb);
+    snprintf(name_h, cap, "%s<%d,%d%s>", L->aff_reslab ? "k_apply_affine2" : (L->aff_shfl ? "k_apply_affine_shfl" : "k_apply_affine"),
+             L->P, L->tma_tpb, L->aff_reslab == 2 ? ",warp-local" : "");
   else if (L->lay.mode == 1 && L->use_tma)
     snprintf(name_h, cap, "k_apply_tma<%d,%d,%d>", L->P, L->tma_tpb, L->tma_r);
   else if (L->lay.mode == 1)

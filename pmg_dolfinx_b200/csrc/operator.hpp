@@ -14,6 +14,10 @@ struct pmgx_halo
   cudaEvent_t ev_ready = nullptr; // compute stream -> comm stream (x is ready to pack)
   cudaEvent_t ev_done = nullptr;  // comm stream -> compute stream (ghosts are in place)
   bool in_flight = false;
+  // small exchanges (AMG levels): pack, wait and unpack run on the compute stream itself -- no comm-stream
+  // hop, no events; set by the owner of the plan, peer-memory path only
+  bool single_stream = false;
+  double* pending_x = nullptr; // single-stream exchange begun, wait + unpack outstanding
   // NVLink peer-memory path (halo.cu, p2p.cu): packed values are stored straight into the
   // destination rank's receive buffer; an epoch flag per source rank signals completion
   bool p2p = false;
