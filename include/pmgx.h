@@ -291,7 +291,10 @@ int pmgx_amg_setup_dist_h(int rank, int nranks, int n_owned, int n_ghost, const 
                           pmgx_allgather_fn allgather, void* user, int min_coarse, int max_levels,
                           pmgx_amg_hier** out);
 /* out_h[0]=n_owned [1]=n_ghost [2]=n_send_nbr [3]=n_send [4]=n_recv_nbr [5]=n_recv
- * [6]=1 if this (coarsest) level holds rows of the dense inverse [7]=global rows of the level [8]=nnz(R_l) */
+ * [6]=1 if this (coarsest) level holds rows of the dense inverse [7]=global rows of the level [8]=nnz(R_l)
+ * [9]=1 if the level is REPLICATED (levels with at most PMGX_AMG_REPL_CAP = 65536 rows on the whole machine
+ * live completely on every rank: n_owned = global size, no ghosts; the parent's P then addresses the
+ * rank-ordered global numbering) [10]=rows of a first replicated level that this rank's restriction produces */
 int pmgx_amg_level_dist_sizes(pmgx_amg_hier* h, int level, long long* out_h);
 /* R_l = the rows of the global P_l^T this rank owns: (columns of P_l that are owned) x (n_owned + n_ghost)
  * CSR; with one rank R_l = P_l^T.  P_l's own columns >= its owned count address the next level's ghosts. */

@@ -43,6 +43,14 @@ k_dense_rows(int n_rows, int n_cols, const double* __restrict__ inv, const doubl
     x[row] = s;
 }
 
+// out[g] = in[perm[g]]
+__global__ void k_permute(int n, const int32_t* __restrict__ perm, const double* __restrict__ in, double* __restrict__ out)
+{
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n)
+    out[g] = in[perm[g]];
+}
+
 struct RectCsr
 {
   int n_rows = 0;
@@ -93,6 +101,12 @@ struct AmgPrecond : Precond
     int n_global = 0;
     DevBuf<double> inv;
     pmgx_halo* gather = nullptr; // owned
+    // first replicated level: all-gather of the restricted residual, then the canonical ordering
+    bool repl_first = false;
+    int n_mine = 0;
+    pmgx_halo* repl_gather = nullptr; // owned
+    DevBuf<double> bg;                // [mine | the others in rank order]
+    DevBuf<int32_t> perm;             // canonical index -> position in bg
   };
   pmgx_ctx* ctx = nullptr;
   std::vector<Lv> lv;
@@ -113,6 +127,8 @@ struct AmgPrecond : Precond
         pmgx_halo_destroy(L.halo);
       if (L.gather)
         pmgx_halo_destroy(L.gather);
+      if (L.repl_gather)
+        pmgx_halo_destroy(L.repl_gather);
     }
   }
 
@@ -150,7 +166,18 @@ struct AmgPrecond : Precond
       halo_fwd_begin(L.halo_v, L.sm->r.p);
       halo_fwd_end(L.halo_v, L.sm->r.p);
     }
-    spmv_rect(ctx, C.n_owned, L.R.ptr.p, L.R.cols.p, L.R.vals.p, L.sm->r.p, C.b.p, false, 32); // b_c = P^T r
+    if (C.repl_first)
+    {
+      // the next level lives completely on every rank: my part of b_c, all-gather, canonical order
+      spmv_rect(ctx, C.n_mine, L.R.ptr.p, L.R.cols.p, L.R.vals.p, L.sm->r.p, C.bg.p, false, 32);
+      halo_fwd_begin(C.repl_gather, C.bg.p);
+      halo_fwd_end(C.repl_gather, C.bg.p);
+      k_permute<<<(C.n_owned + 255) / 256, 256, 0, ctx->stream>>>(C.n_owned, C.perm.p, C.bg.p, C.b.p);
+      check_launch("k_permute");
+      count_launch(ctx);
+    }
+    else
+      spmv_rect(ctx, C.n_owned, L.R.ptr.p, L.R.cols.p, L.R.vals.p, L.sm->r.p, C.b.p, false, 32); // b_c = P^T r
     cycle(l + 1, C.b.p, C.x.p);
     if (gamma == 2 && l + 2 < (int)lv.size())
     {
@@ -285,8 +312,21 @@ int pmgx_coarse_create_amg(pmgx_ctx* ctx, pmgx_operator* A, int max_iter, double
     }
     else
     {
-      D.halo = pmgx::make_halo(ctx, L.n_owned, L.n_ghost, L.plan); // collective: same order on every rank
-      D.halo_v = D.halo;
+      if (!L.replicated)
+      {
+        D.halo = pmgx::make_halo(ctx, L.n_owned, L.n_ghost, L.plan); // collective: same order on every rank
+        D.halo_v = D.halo;
+      }
+      else if (L.n_mine > 0 || !L.gather_perm.empty())
+      {
+        // first replicated level (collective as well)
+        D.repl_first = true;
+        D.n_mine = L.n_mine;
+        D.repl_gather = pmgx::make_halo(ctx, L.n_mine, L.n_owned - L.n_mine, L.repl_plan);
+        D.bg.alloc((size_t)std::max(L.n_owned, 1));
+        PMGX_CUDA(cudaMemsetAsync(D.bg.p, 0, (size_t)std::max(L.n_owned, 1) * sizeof(double), ctx->stream));
+        D.perm.upload(L.gather_perm.data(), L.gather_perm.size(), ctx->stream);
+      }
       std::vector<int32_t> off((size_t)L.n_owned);
       for (int i = 0; i < L.n_owned; ++i)
       {
@@ -332,7 +372,8 @@ int pmgx_coarse_create_amg(pmgx_ctx* ctx, pmgx_operator* A, int max_iter, double
       D.n_global = (int)L.n_global;
       D.inv.upload(L.inv_rows.data(), L.inv_rows.size(), ctx->stream);
       const int n_gather = (int)L.n_global - L.n_owned;
-      D.gather = pmgx::make_halo(ctx, L.n_owned, n_gather, L.gather_plan);
+      if (!L.replicated)
+        D.gather = pmgx::make_halo(ctx, L.n_owned, n_gather, L.gather_plan);
       const size_t nt = (size_t)L.n_owned + std::max(L.n_ghost, n_gather);
       D.b.alloc(nt);
       if (nt > 0)

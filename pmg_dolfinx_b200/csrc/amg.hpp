@@ -56,6 +56,15 @@ struct Level
   double lmax = 1.0; // 1.1 * lambda_max(D^-1 A), power iteration
   std::vector<int> ghost_src;      // per ghost: owning rank
   std::vector<int32_t> ghost_rid;  // per ghost: index on the owning rank
+  // replicated levels (small on the whole machine): the complete level lives on every rank, n_owned = its global
+  // size, no ghosts, no halo.  The FIRST replicated level is entered through an all-gather of the restricted
+  // residual: n_mine entries of it come from this rank's restriction, repl_plan brings the others,
+  // gather_perm[g] = position of canonical index g in the gather layout [mine | others in rank order].  The
+  // parent level's P addresses the canonical numbering directly.
+  bool replicated = false;
+  int n_mine = 0;
+  std::vector<int32_t> gather_perm;
+  Plan repl_plan;
   // coarsest level only: rows of the dense inverse of the gathered matrix, columns in this rank's
   // vector layout [owned | all other ranks' entries in rank order] (= gather_plan's ghost block)
   bool dense = false;

@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <numeric>
@@ -501,8 +502,109 @@ void setup(Hierarchy& H, Csr A0, int n_owned, int n_ghost, const Plan& plan0, co
     }
   }
 
+  const long long repl_cap = getenv("PMGX_AMG_REPL_CAP") ? atoll(getenv("PMGX_AMG_REPL_CAP")) : 65536;
   while (true)
   {
+    // ---- a level that is small on the whole machine is REPLICATED: every rank gathers the complete level
+    // matrix and builds the rest of the hierarchy for itself (deterministic, hence identical everywhere).
+    // Below this point a cycle needs no communication at all -- one all-gather of the restricted residual
+    // replaces ~6 latency-bound halo exchanges per level and application.
+    if (cm.nranks > 1 && !H.levels.empty())
+    {
+      std::vector<long long> counts((size_t)cm.nranks, 0), off((size_t)cm.nranks + 1, 0);
+      long long mine = L.n_owned;
+      cm.allgather(&mine, sizeof(mine), counts.data());
+      for (int r = 0; r < cm.nranks; ++r)
+        off[r + 1] = off[r] + counts[r];
+      const long long ng = off[cm.nranks];
+      if (ng > 0 && ng <= repl_cap)
+      {
+        auto canon = [&](int32_t c) -> long long
+        { return c < L.n_owned ? off[cm.rank] + c : off[L.ghost_src[c - L.n_owned]] + L.ghost_rid[c - L.n_owned]; };
+        std::vector<char> blob;
+        put1<long long>(blob, L.A.nnz());
+        for (int i = 0; i < L.n_owned; ++i)
+          for (int32_t j = L.A.ptr[i]; j < L.A.ptr[i + 1]; ++j)
+          {
+            put1<int32_t>(blob, (int32_t)(off[cm.rank] + i));
+            put1<int32_t>(blob, (int32_t)canon(L.A.cols[j]));
+            put1<double>(blob, L.A.vals[j]);
+          }
+        auto all = allgather_var(cm, blob);
+        std::vector<std::map<int32_t, double>> rows((size_t)ng);
+        for (auto& bl : all)
+        {
+          Reader rd{bl.data(), bl.data() + bl.size()};
+          const long long nz = rd.get1<long long>();
+          for (long long t = 0; t < nz; ++t)
+          {
+            const int32_t r = rd.get1<int32_t>(), c = rd.get1<int32_t>();
+            rows[r][c] += rd.get1<double>();
+          }
+        }
+        Csr Ag;
+        Ag.n_rows = Ag.n_cols = (int)ng;
+        Ag.ptr.assign((size_t)ng + 1, 0);
+        for (long long r = 0; r < ng; ++r)
+        {
+          for (auto& e : rows[r])
+          {
+            Ag.cols.push_back(e.first);
+            Ag.vals.push_back(e.second);
+          }
+          Ag.ptr[r + 1] = (int32_t)Ag.cols.size();
+        }
+        // the parent's prolongator now addresses the canonical (rank-ordered) numbering of the gathered level
+        Level& parent = H.levels.back();
+        {
+          std::vector<std::pair<int32_t, double>> row;
+          for (int i = 0; i < parent.P.n_rows; ++i)
+          {
+            row.clear();
+            for (int32_t j = parent.P.ptr[i]; j < parent.P.ptr[i + 1]; ++j)
+              row.emplace_back((int32_t)canon(parent.P.cols[j]), parent.P.vals[j]);
+            std::sort(row.begin(), row.end(), [](const std::pair<int32_t, double>& a, const std::pair<int32_t, double>& b)
+                      { return a.first < b.first; });
+            for (int32_t j = parent.P.ptr[i], t = 0; j < parent.P.ptr[i + 1]; ++j, ++t)
+              parent.P.cols[j] = row[t].first, parent.P.vals[j] = row[t].second;
+          }
+          parent.P.n_cols = (int)ng;
+        }
+        Hierarchy sub;
+        Comm self;
+        setup(sub, std::move(Ag), (int)ng, 0, Plan(), self, min_coarse, std::max(1, max_levels - (int)H.levels.size()));
+        Level& first = sub.levels.front();
+        first.n_mine = L.n_owned;
+        // all-gather plan of the restricted residual (every rank sends its owned entries to every other rank) and
+        // the position of every canonical index in this rank's gather layout [mine | the others in rank order]
+        int slot = 0;
+        first.gather_perm.assign((size_t)ng, 0);
+        for (int i = 0; i < L.n_owned; ++i)
+          first.gather_perm[(size_t)(off[cm.rank] + i)] = i;
+        for (int r = 0; r < cm.nranks; ++r)
+        {
+          if (r == cm.rank)
+            continue;
+          first.repl_plan.send_ranks.push_back(r);
+          for (int i = 0; i < L.n_owned; ++i)
+            first.repl_plan.send_idx.push_back(i);
+          first.repl_plan.send_offsets.push_back((int)first.repl_plan.send_idx.size());
+          first.repl_plan.recv_ranks.push_back(r);
+          for (long long t = 0; t < counts[r]; ++t)
+          {
+            first.gather_perm[(size_t)(off[r] + t)] = L.n_owned + slot;
+            first.repl_plan.recv_idx.push_back(slot++);
+          }
+          first.repl_plan.recv_offsets.push_back((int)first.repl_plan.recv_idx.size());
+        }
+        for (Level& S : sub.levels)
+        {
+          S.replicated = true;
+          H.levels.push_back(std::move(S));
+        }
+        return;
+      }
+    }
     const Csr& M = L.A;
     const int n = L.n_owned;
     const std::vector<double> d = diagonal(M);
@@ -979,6 +1081,8 @@ int pmgx_amg_level_dist_sizes(pmgx_amg_hier* h, int level, long long* out_h)
   out_h[6] = L.dense ? 1 : 0;
   out_h[7] = L.n_global;
   out_h[8] = L.R.nnz();
+  out_h[9] = L.replicated ? 1 : 0;
+  out_h[10] = L.n_mine;
   PMGX_API_END
 }
 

@@ -23,7 +23,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PGRID = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
 
 
-def _worker(rank, world, port, n, out):
+def _worker(rank, world, port, n, out, repl_cap):
+    os.environ["PMGX_AMG_REPL_CAP"] = str(repl_cap)
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "scripts"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -68,11 +69,11 @@ def _worker(rank, world, port, n, out):
                                     ctypes.cast(allgather, ctypes.c_void_p), None, 60, 10, ctypes.addressof(h)))
     levels = []
     for l in range(lib.pmgx_amg_num_levels(h)):
-        sz, ds = np.zeros(4, dtype=np.int64), np.zeros(9, dtype=np.int64)
+        sz, ds = np.zeros(4, dtype=np.int64), np.zeros(11, dtype=np.int64)
         check(lib.pmgx_amg_level_sizes(h, l, ptr(sz)))
         check(lib.pmgx_amg_level_dist_sizes(h, l, ptr(ds)))
         nrow, nnz, pc, pnnz = (int(v) for v in sz)
-        lo, lg, nsn, ns, nrn, nr, dense, nglob, rnnz = (int(v) for v in ds)
+        lo, lg, nsn, ns, nrn, nr, dense, nglob, rnnz, repl, n_mine = (int(v) for v in ds)
         assert lo == nrow
         ap, ac, av = np.zeros(nrow + 1, np.int32), np.zeros(nnz, np.int32), np.zeros(nnz)
         pp, pcl, pv = np.zeros(nrow + 1, np.int32), np.zeros(pnnz, np.int32), np.zeros(pnnz)
@@ -90,7 +91,7 @@ def _worker(rank, world, port, n, out):
             check(lib.pmgx_amg_level_get_restriction(h, l, ptr(rp), ptr(rc), ptr(rv)))
         levels.append(dict(n_owned=lo, n_ghost=lg, A=(ap, ac, av), P=(pp, pcl, pv, pc), R=(rp, rc, rv), lmax=lmax.value,
                            ghost_src=gs, ghost_rid=gr, send=(psr, pso, psi), recv=(prr, pro, pri), dense=dense,
-                           n_global=nglob, inv=inv))
+                           n_global=nglob, inv=inv, replicated=bool(repl), n_mine=n_mine))
     check(lib.pmgx_amg_destroy(h))
     objs = [None] * world if rank == 0 else None
     dist.gather_object(dict(levels=levels, l2g=s.l2g[:no]), objs, dst=0)
@@ -103,6 +104,12 @@ def _worker(rank, world, port, n, out):
 
 def _gcols(per_rank, l):
     """per rank: local column (owned + ghost) -> global id of level l, and the row offsets"""
+    if per_rank[0]["levels"][l]["replicated"]:
+        # the whole level on every rank in the canonical numbering; rows this rank's restriction produces: n_mine
+        ng = per_rank[0]["levels"][l]["n_owned"]
+        first = not per_rank[0]["levels"][l - 1]["replicated"]
+        no = [r["levels"][l]["n_mine"] for r in per_rank] if first else [ng] + [0] * (len(per_rank) - 1)
+        return [np.arange(ng, dtype=np.int64) for _ in per_rank], np.concatenate([[0], np.cumsum(no)]), no
     no = [r["levels"][l]["n_owned"] for r in per_rank]
     off = np.concatenate([[0], np.cumsum(no)])
     out = []
@@ -120,6 +127,21 @@ def _assemble(per_rank, l):
     """Global A_l, P_l, R_l and row offsets of level l from the ranks' pieces."""
     gc, off, no = _gcols(per_rank, l)
     N = int(off[-1])
+    if per_rank[0]["levels"][l]["replicated"]:
+        # identical copies on every rank; rank 0's stands for the level
+        mats = []
+        for r in per_rank:
+            ap, ac, av = r["levels"][l]["A"]
+            mats.append(sp.csr_matrix((av, ac, ap), shape=(N, N)))
+        assert all(abs(m - mats[0]).max() == 0 for m in mats[1:])
+        A = mats[0]
+        P = R = None
+        pp, pcl, pv, pc = per_rank[0]["levels"][l]["P"]
+        if pc:
+            P = sp.csr_matrix((pv, pcl, pp), shape=(N, pc))
+            rp, rc, rv = per_rank[0]["levels"][l]["R"]
+            R = sp.csr_matrix((rv, rc, rp), shape=(pc, N))
+        return A, P, off, R
     Ar, Ac_, Av = [], [], []
     for q, r in enumerate(per_rank):
         ap, ac, av = r["levels"][l]["A"]
@@ -133,7 +155,10 @@ def _assemble(per_rank, l):
         Pr, Pc, Pv, Rr, Rc, Rv = [], [], [], [], [], []
         for q, r in enumerate(per_rank):
             pp, pcl, pv, pc = r["levels"][l]["P"]
-            assert pc == nc[q] + r["levels"][l + 1]["n_ghost"]     # P's columns: the next level's owned + ghost dofs
+            if r["levels"][l + 1]["replicated"]:
+                assert pc == r["levels"][l + 1]["n_owned"]           # ... or the canonical numbering of a replicated level
+            else:
+                assert pc == nc[q] + r["levels"][l + 1]["n_ghost"]   # P's columns: the next level's owned + ghost dofs
             Pr.append(off[q] + np.repeat(np.arange(no[q]), np.diff(pp)))
             Pc.append(gcc[q][pcl])
             Pv.append(pv)
@@ -146,16 +171,19 @@ def _assemble(per_rank, l):
     return A, P, off, R
 
 
+@pytest.mark.parametrize("repl_cap", [0, 65536], ids=["distributed-to-the-bottom", "small-levels-replicated"])
 @pytest.mark.parametrize("world", [2, 4])
-def test_distributed_amg_setup_over_gloo(world, tmp_path):
+def test_distributed_amg_setup_over_gloo(world, repl_cap, tmp_path):
     sys.path.insert(0, os.path.join(ROOT, "scripts"))
     import prototype_sa_amg as proto
     n = (12, 12, 12)
     out = str(tmp_path / "amg.pkl")
-    mp.spawn(_worker, args=(world, 29720 + world, n, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, 29720 + world + (10 if repl_cap else 0), n, out, repl_cap), nprocs=world, join=True)
     per_rank = pickle.load(open(out, "rb"))
     nl = len(per_rank[0]["levels"])
     assert nl >= 2 and all(len(r["levels"]) == nl for r in per_rank)
+    assert any(L["replicated"] for L in per_rank[0]["levels"]) == bool(repl_cap)
+    assert not per_rank[0]["levels"][0]["replicated"]
     Ag, bcg = proto.p1_matrix(n[0])
     # level 0 in the gathered numbering is a permutation of the oracle matrix
     A0, P0, off0, _ = _assemble(per_rank, 0)
@@ -182,7 +210,8 @@ def test_distributed_amg_setup_over_gloo(world, tmp_path):
             coff = np.concatenate([[0], np.cumsum([r["levels"][l + 1]["n_owned"] for r in per_rank])])
             ranks_of_col = np.searchsorted(coff, np.arange(P.shape[1]), side="right") - 1
             Pc = P.tocoo()
-            assert (ranks_of_row[Pc.row] != ranks_of_col[Pc.col]).any()       # P does reach across ranks
+            if not per_rank[0]["levels"][l]["replicated"] and not per_rank[0]["levels"][l + 1]["replicated"]:
+                assert (ranks_of_row[Pc.row] != ranks_of_col[Pc.col]).any()   # P does reach across ranks
             free = np.diff(A.indptr) > 1
             interior = np.abs(A @ np.ones(A.shape[0])) <= 1e-12 * A.diagonal()
             rs = np.asarray(P.sum(axis=1)).ravel()
@@ -190,6 +219,8 @@ def test_distributed_amg_setup_over_gloo(world, tmp_path):
             assert not (np.diff(P.indptr)[~free] > 0).any()                  # Dirichlet rows stay out
         # halo plans: what q sends to d is exactly what d expects from q, in order
         for q, r in enumerate(per_rank):
+            if r["levels"][l]["replicated"]:
+                continue
             L = r["levels"][l]
             sr, so, si = L["send"]
             for k, d in enumerate(sr):
@@ -209,10 +240,14 @@ def test_distributed_amg_setup_over_gloo(world, tmp_path):
     Ac, _, off, _ = _assemble(per_rank, nl - 1)
     N = Ac.shape[0]
     inv = np.zeros((N, N))
-    for q, L in enumerate(last):
-        no = L["n_owned"]
-        loc2glob = np.concatenate([np.arange(off[q], off[q + 1])] + [np.arange(off[p], off[p + 1]) for p in range(world) if p != q])
-        inv[off[q]:off[q + 1], loc2glob] = L["inv"].reshape(no, N)
+    if last[0]["replicated"]:
+        assert all(np.array_equal(L["inv"], last[0]["inv"]) for L in last)
+        inv = last[0]["inv"].reshape(N, N)
+    else:
+        for q, L in enumerate(last):
+            no = L["n_owned"]
+            loc2glob = np.concatenate([np.arange(off[q], off[q + 1])] + [np.arange(off[p], off[p + 1]) for p in range(world) if p != q])
+            inv[off[q]:off[q + 1], loc2glob] = L["inv"].reshape(no, N)
     assert np.allclose(inv @ Ac.toarray(), np.eye(N), atol=1e-9)
     levels[-1]["dense"] = inv
     # the hierarchy does its job: a handful of PCG iterations, like the single-rank one
