@@ -111,7 +111,8 @@ struct AmgPrecond : Precond
   pmgx_ctx* ctx = nullptr;
   std::vector<Lv> lv;
   int nu = 2;
-  int gamma = 1; // cycle index below level 0: 1 = V, 2 = W (two coarse visits; the small levels are latency, not bandwidth)
+  int gamma = 1; // cycle index: 1 = V, 2 = W (two coarse visits; the small levels are latency, not bandwidth)
+  int gamma_from = 0; // first level whose coarse level is visited gamma times
 
   ~AmgPrecond() override
   {
@@ -179,7 +180,7 @@ struct AmgPrecond : Precond
     else
       spmv_rect(ctx, C.n_owned, L.R.ptr.p, L.R.cols.p, L.R.vals.p, L.sm->r.p, C.b.p, false, 32); // b_c = P^T r
     cycle(l + 1, C.b.p, C.x.p);
-    if (gamma == 2 && l + 2 < (int)lv.size())
+    if (gamma == 2 && l >= gamma_from && l + 2 < (int)lv.size())
     {
       // W-cycle: a second visit on the coarse residual, x_c += B_c (b_c - A_c x_c)  (symmetric: 2B - BAB)
       C.A->apply(C.x.p, C.r2.p);
@@ -289,6 +290,8 @@ int pmgx_coarse_create_amg(pmgx_ctx* ctx, pmgx_operator* A, int max_iter, double
     nu_coarse = std::min(std::max(atoi(e), 1), 8);
   if (const char* e = getenv("PMGX_AMG_GAMMA"))
     M->gamma = atoi(e) == 2 ? 2 : 1;
+  if (const char* e = getenv("PMGX_AMG_GAMMA_FROM"))
+    M->gamma_from = std::max(atoi(e), 0);
   const bool use_lp = !(getenv("PMGX_AMG_LP") && atoi(getenv("PMGX_AMG_LP")) == 0);
   // first level whose smoother runs the fused SpMV + Chebyshev kernels.  Measured at 1.59 M rows (coarse solve,
   // 9 iterations): fused everywhere 7.56 ms, from level 1 on 7.08 ms, nowhere 7.25 ms -- on level 0 the

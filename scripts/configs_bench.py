@@ -81,14 +81,30 @@ def config2(ctx):
         torch.cuda.empty_cache()
 
 
-def make_level(ctx, P, ndofs):
-    n = api.boxmesh_fit(ndofs, P)
-    m = api.BoxMesh(n)
-    sp = m.space(P)
-    d = dict(mesh=m, sp=sp, dm=ctx.to_device(sp.dofmap), xg=ctx.to_device(m.xgeom), gd=ctx.to_device(m.geom_dofmap),
+PGRID = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+RANK, WORLD = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def make_level(ctx, P, ndofs, want_coords=False):
+    """ndofs per rank (weak scaling: the mesh-fit routine runs on ndofs * world, examples/cg/main.cpp:288-310)"""
+    n = api.boxmesh_fit(ndofs * WORLD, P)
+    m = api.BoxMesh(n, PGRID[WORLD], RANK)
+    sp = m.space(P, want_coords=want_coords)
+    halo = api.Halo.from_space(ctx, sp) if WORLD > 1 else None
+    d = dict(mesh=m, sp=sp, halo=halo, dm=ctx.to_device(sp.dofmap), xg=ctx.to_device(m.xgeom), gd=ctx.to_device(m.geom_dofmap),
              kap=torch.full((m.n_cells,), 2.0, dtype=torch.float64, device=ctx.device), bc=ctx.to_device(sp.bc))
-    d["op"] = api.MatFreeLaplacian(ctx, P, d["kap"], d["dm"], d["xg"], d["gd"], m.lcells, m.bcells, d["bc"], sp.n_owned)
+    d["op"] = api.MatFreeLaplacian(ctx, P, d["kap"], d["dm"], d["xg"], d["gd"], m.lcells, m.bcells, d["bc"], sp.n_owned,
+                                   sp.n_ghost, halo)
     return d
+
+
+def rank_max(ctx, ms):
+    if WORLD == 1:
+        return ms
+    import torch.distributed as dist
+    t = torch.tensor([ms], dtype=torch.float64, device=ctx.device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
 
 
 def b_apply(P, ncells, ndofs):
@@ -146,18 +162,21 @@ def config3(ctx):
 
 
 def config4(ctx):
+    """examples/cg at P6, ~200 M dofs per GPU on 1/2/4/8 GPUs (run under torchrun for more than one): Jacobi-CG with
+    b = 1, x0 = 0, 20 its, rtol 1e-6 (examples/cg/main.cpp:238-249), then 30 Chebyshev iterations on the problem of
+    :136-158,234-236,268-284: f = 1000 exp(-((x-.5)^2+(y-.5)^2)/0.02), g = 1.3 with lifting, x0 = 1 with the BC set."""
     P = 6
-    d = make_level(ctx, P, 200_000_000)
+    d = make_level(ctx, P, 200_000_000, want_coords=True)
     sp, m, op = d["sp"], d["mesh"], d["op"]
-    x, b = api.Vector(ctx, sp.n_owned), api.Vector(ctx, sp.n_owned)
+    x, b = api.Vector(ctx, sp.n_owned, sp.n_ghost, d["halo"]), api.Vector(ctx, sp.n_owned, sp.n_ghost, d["halo"])
     b.set(1.0)
-    cg = api.CGSolver(ctx, sp.n_owned, 0)
+    cg = api.CGSolver(ctx, sp.n_owned, sp.n_ghost)
     cg.set_max_iterations(20)
     cg.set_tolerance(1e-6)
     cg.store_coefficients(True)
     cg.solve(op, x, b)                       # warm-up
     x.set(0.0)
-    cg2 = api.CGSolver(ctx, sp.n_owned, 0)
+    cg2 = api.CGSolver(ctx, sp.n_owned, sp.n_ghost)
     cg2.set_max_iterations(20)
     cg2.set_tolerance(1e-6)
     cg2.store_coefficients(True)
@@ -167,23 +186,33 @@ def config4(ctx):
     its = cg2.solve(op, x, b)
     e1.record(ctx.stream)
     ctx.sync()
-    ms_cg = e0.elapsed_time(e1)
+    ms_cg = rank_max(ctx, e0.elapsed_time(e1))
     eig = cg2.compute_eigenvalues()
-    ms_apply = timed(ctx, lambda: op(b, x), 10)
-    B = b_apply(P, m.n_cells, sp.n_owned)
-    ch = api.Chebyshev(ctx, sp.n_owned, 0, (0.1 * eig[-1], 1.1 * eig[-1]))
+    ms_apply = rank_max(ctx, timed(ctx, lambda: op(b, x), 10))
+    B = b_apply(P, m.n_owned_cells, sp.n_owned) * WORLD
+    ch = api.Chebyshev(ctx, sp.n_owned, sp.n_ghost, (0.1 * eig[-1], 1.1 * eig[-1]))
     ch.set_max_iterations(30)
-    x.set(1.0)
+    X = sp.coords
+    f = 1000.0 * np.exp(-((X[:, 0] - 0.5) ** 2 + (X[:, 1] - 0.5) ** 2) / 0.02)
+    op.assemble_rhs(ctx.to_device(f), 1.3, b)                       # assemble + lifting + set_bc (g = 1.3)
+    def start():
+        x.set(1.0)
+        x.data[: sp.n_owned + sp.n_ghost][d["bc"].bool()] = 1.3      # set_bc on the initial guess (:280-281)
+    start()
     ch.solve(op, x, b)
-    x.set(1.0)
+    start()
     ctx.sync()
     e0.record(ctx.stream)
     ch.solve(op, x, b)
     e1.record(ctx.stream)
     ctx.sync()
-    ms_ch = e0.elapsed_time(e1)
-    n = sp.n_owned
-    print(json.dumps({"config": 4, "P": P, "cells": list(m.n), "ndofs": n, "cg_iterations": its,
+    ms_ch = rank_max(ctx, e0.elapsed_time(e1))
+    res = ch.residual(op, x, b)
+    n = sp.n_global
+    if RANK != 0:
+        return
+    print(json.dumps({"config": 4, "n_gpus": WORLD, "P": P, "cells": list(m.n), "ndofs": n, "cg_iterations": its,
+                      "kernel": op.kernel_name(), "chebyshev_residual_after_30": res,
                       "cg_ms_per_iteration": round(ms_cg / its, 3), "cg_gdofs_per_iteration": round(n * its / ms_cg / 1e6, 2),
                       "cg_algorithmic_gbs": round((B + 104 * n) * its / ms_cg / 1e6, 1),
                       "cg_frac_of_hbm_peak": round((B + 104 * n) * its / ms_cg / 1e6 / PEAK, 3),
@@ -196,7 +225,20 @@ def config4(ctx):
 
 if __name__ == "__main__":
     which = [int(a) for a in sys.argv[1:]] or [2, 3, 4]
-    ctx = api.Context(0)
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    nccl_id = None
+    if WORLD > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        box = [api.Context.nccl_unique_id() if RANK == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        nccl_id = box[0]
+    ctx = api.Context(local, RANK, WORLD, nccl_id)
     for c in which:
         {2: config2, 3: config3, 4: config4}[c](ctx)
         torch.cuda.empty_cache()
+    if WORLD > 1:
+        ctx.sync()
+        dist.barrier()
+        dist.destroy_process_group()

@@ -31,13 +31,17 @@ def _setup(ctx, n, min_coarse, nu=2, rtol=1e-8, max_iter=60):
     return api, proto, A, bc, nd, op, cs
 
 
+@pytest.mark.parametrize("fuse_from", [0, 1, 99], ids=["fused-smoother-all-levels", "fused-from-level-1", "unfused"])
 @pytest.mark.parametrize("lp", [False, True], ids=["fp64-matrix", "fp32-int16-smoother-matrix"])
 @pytest.mark.parametrize("n,nu", [(8, 2), (16, 2), (16, 1), (20, 3)])
-def test_device_cycle_equals_numpy_cycle_on_the_same_hierarchy(ctx, n, nu, lp, monkeypatch):
+def test_device_cycle_equals_numpy_cycle_on_the_same_hierarchy(ctx, n, nu, lp, fuse_from, monkeypatch):
     """lp: the level-0 smoother streams the matrix with FP32 values and 16-bit column deltas (the default):
     the cycle is then the exact cycle of a matrix rounded to FP32, i.e. equal to 1e-6 instead of 1e-10."""
     from test_amg_setup import _hierarchy
     monkeypatch.setenv("PMGX_AMG_LP", "1" if lp else "0")
+    # which levels run the SpMV with the Chebyshev update as its epilogue (csr.cu k_spmv_cheb): all of them, the
+    # default (levels >= 1), none -- the three must agree with the numpy cycle
+    monkeypatch.setenv("PMGX_AMG_FUSE_FROM", str(fuse_from))
     tol = 2e-6 if lp else 1e-10
     api, proto, A, bc, nd, op, cs = _setup(ctx, n, 100, nu=nu)
     levels = _hierarchy(A, min_coarse=100, max_levels=12)
