@@ -391,6 +391,16 @@ int pmgx_ghostmesh_halo_lists(pmgx_ghostmesh* m, int degree, int* send_ranks_h, 
  * evaluated by the caller: fvals[n_owned+n_ghost] device array of f at the dof coordinates.
  * Result is complete on owned dofs (ghost cells contribute, like the operator). */
 int pmgx_laplacian_rhs(pmgx_operator* lap, const double* fvals, double g, double* b);
+/* Dirichlet marker of all exterior facets, on the device (mesh::exterior_facet_indices +
+ * fem::locate_dofs_topological on the host in the reference, examples/pmg/main.cpp:173-185): marker_out[i] = 1
+ * for every dof on a facet that belongs to exactly one cell, owned and ghost entries alike.  geom_dofmap
+ * [n_cells][8] (tp vertex order), dofmap[n_cells][(P+1)^3] are device arrays over the owned + ghost cells of
+ * a ghost-layer mesh (src/mesh.hpp:16-98); halo: the forward-scatter plan of the space (NULL on one rank) --
+ * facet counts are exact for owned dofs, the ghost entries are taken from their owners.  COLLECTIVE like any
+ * halo update. */
+int pmgx_bc_marker_exterior(pmgx_ctx* ctx, int degree, int n_cells, const int32_t* geom_dofmap,
+                            const int32_t* dofmap, int n_owned, int n_ghost, pmgx_halo* halo, int8_t* marker_out);
+
 /* fem::apply_lifting + set_bc for inhomogeneous Dirichlet data (examples/pmg/main.cpp:293-295,
  * examples/cg/main.cpp:235-237): b -= A_full g_bc on the owned rows, where A_full is this operator
  * without its Dirichlet rows/columns and g_bc = gvals at the marked dofs, 0 elsewhere; then b = gvals at

@@ -79,6 +79,15 @@ def gll_interp_1d(pc, pf):
     return M.reshape(pf + 1, pc + 1)
 
 
+def exterior_bc_marker(ctx, degree, geometry_dofmap, dofmap, n_owned, n_ghost=0, halo=None):
+    """Device int8 marker of the dofs on exterior facets (examples/pmg/main.cpp:173-185), owned + ghost."""
+    out = torch.zeros(int(n_owned) + int(n_ghost), dtype=torch.int8, device=ctx.device)
+    n_cells = int(geometry_dofmap.numel() // 8)
+    check(lib.pmgx_bc_marker_exterior(ctx.h, degree, n_cells, ptr(geometry_dofmap), ptr(dofmap), int(n_owned), int(n_ghost),
+                                      halo.h if halo is not None else None, ptr(out)))
+    return out
+
+
 def tqli(d, e):
     d = _np(d, np.float64).copy()
     e = _np(e, np.float64).copy()

@@ -96,7 +96,12 @@ def run_check(api, ctx, rank, world, n=(9, 8, 7), perturb=0.15, log=print, gener
         halo = api.Halo.from_space(ctx, sp) if world > 1 else None
         dm, bc = ctx.to_device(sp.dofmap), ctx.to_device(sp.bc)
         op = api.MatFreeLaplacian(ctx, P, kappa, dm, xgeom, gdm, mesh.lcells, mesh.bcells, bc, sp.n_owned, sp.n_ghost, halo)
-        lv.append(dict(P=P, sp=sp, halo=halo, dm=dm, bc=bc, op=op))
+        # exterior-facet marker built on the device (owned + ghost entries) against the host builder's
+        bc_dev = api.exterior_bc_marker(ctx, P, gdm, dm, sp.n_owned, sp.n_ghost, halo)
+        bad = torch.tensor([int((bc_dev != bc).sum().item())], device=ctx.device)
+        if world > 1:
+            dist.all_reduce(bad)
+        lv.append(dict(P=P, sp=sp, halo=halo, dm=dm, bc=bc, op=op, bc_mismatch=int(bad.item())))
 
     transport = "none"
     if world > 1:
@@ -158,6 +163,10 @@ def run_check(api, ctx, rank, world, n=(9, 8, 7), perturb=0.15, log=print, gener
         eigs.append(eig[-1])
         if rank == 0:
             o = O[li]
+            good = L["bc_mismatch"] == 0
+            ok = ok and good
+            checks[f"P{P} device BC marker mismatches"] = L["bc_mismatch"]
+            log(f"[mgpu x{world}] P{P} device exterior-facet BC marker vs host: {L['bc_mismatch']} mismatches  {'ok' if good else 'FAIL'}")
             check(f"P{P} apply", yg, o["A"](xg), 1e-12)
             check(f"P{P} diag inverse", dg, o["dinv"], 1e-13)
             xo, ko, al, be, ho, r0o = osol.cg(o["A"], o["dinv"], np.zeros(o["nd"]), np.ones(o["nd"]), 20, 1e-6)

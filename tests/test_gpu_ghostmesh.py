@@ -13,13 +13,16 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.mark.parametrize("general", [True, False], ids=["general-mesh", "box-mesh"])
 @pytest.mark.parametrize("perturb", [0.0, 0.15], ids=["affine-cells", "perturbed"])
-def test_general_mesh_single_gpu_matches_oracle(ctx, perturb):
+def test_general_mesh_single_gpu_matches_oracle(ctx, perturb, general):
     from pmg_dolfinx_b200 import api
     spec = importlib.util.spec_from_file_location("mgpu_check", os.path.join(ROOT, "scripts", "mgpu_check.py"))
     mc = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mc)
     lines = []
-    res = mc.run_check(api, ctx, 0, 1, n=(5, 4, 4), perturb=perturb, log=lines.append, general=True)
+    res = mc.run_check(api, ctx, 0, 1, n=(5, 4, 4), perturb=perturb, log=lines.append, general=general)
     assert res["ok"], "\n".join(lines)
     assert res["max_err_over_tol"] < 1.0
+    # the run includes the device-built exterior-facet Dirichlet marker (pmgx_bc_marker_exterior) against the host one
+    assert all(v == 0 for k, v in res["checks"].items() if "BC marker" in k) and any("BC marker" in k for k in res["checks"])
