@@ -51,6 +51,42 @@ __global__ void k_permute(int n, const int32_t* __restrict__ perm, const double*
     out[g] = in[perm[g]];
 }
 
+// short-row rectangular matrix as sliced ELL (thread per row): the prolongator has 1..8 entries per row, with
+// 4 lanes per CSR row its apply is a chain of dependent loads per row (85 us at 1.59 M rows under ncu, as much
+// as a level-0 SpMV that moves six times the bytes)
+struct RectSell
+{
+  int n_rows = 0;
+  DevBuf<long long> slice_ptr;
+  DevBuf<int32_t> cols;
+  DevBuf<double> vals;
+  void upload(const amg::Csr& M, cudaStream_t st)
+  {
+    n_rows = M.n_rows;
+    const int ns = (n_rows + 31) / 32;
+    std::vector<long long> sp((size_t)ns + 1, 0);
+    for (int s = 0; s < ns; ++s)
+    {
+      int w = 0;
+      for (int r = s * 32; r < std::min(n_rows, s * 32 + 32); ++r)
+        w = std::max(w, (int)(M.ptr[r + 1] - M.ptr[r]));
+      sp[s + 1] = sp[s] + (long long)w * 32;
+    }
+    std::vector<int32_t> c((size_t)std::max<long long>(sp[ns], 1), 0);
+    std::vector<double> v((size_t)std::max<long long>(sp[ns], 1), 0.0);
+    for (int r = 0; r < n_rows; ++r)
+      for (int32_t j = M.ptr[r], k = 0; j < M.ptr[r + 1]; ++j, ++k)
+      {
+        const size_t p = (size_t)sp[r >> 5] + (size_t)k * 32 + (r & 31);
+        c[p] = M.cols[j];
+        v[p] = M.vals[j];
+      }
+    slice_ptr.upload(sp.data(), sp.size(), st);
+    cols.upload(c.data(), c.size(), st);
+    vals.upload(v.data(), v.size(), st);
+  }
+};
+
 struct RectCsr
 {
   int n_rows = 0;
@@ -93,7 +129,8 @@ struct AmgPrecond : Precond
     pmgx_halo* halo = nullptr; // owned (levels >= 1)
     pmgx_halo* halo_v = nullptr; // borrowed: forward-scatter plan of this level's vectors (level 0: the operator's)
     pmgx_cheb* sm = nullptr;
-    RectCsr P, R;              // to / from the next coarser level
+    RectCsr R;                 // from this level to the next coarser one (rows of P^T: long rows, 32 lanes per row)
+    RectSell P;                // back (short rows, thread per row)
     DevBuf<double> x, b;       // levels >= 1 (and the private b of a dense level)
     DevBuf<double> x2, r2;     // second coarse visit of a W-cycle (levels >= 1)
     long long nnz_p = 0;
@@ -193,7 +230,7 @@ struct AmgPrecond : Precond
       halo_fwd_begin(C.halo_v, C.x.p);
       halo_fwd_end(C.halo_v, C.x.p);
     }
-    spmv_rect(ctx, L.n_owned, L.P.ptr.p, L.P.cols.p, L.P.vals.p, C.x.p, x, true, 4);          // x += P x_c
+    spmv_sell_rect(ctx, L.n_owned, L.P.slice_ptr.p, L.P.cols.p, L.P.vals.p, C.x.p, x, true); // x += P x_c
     cheb_solve(L.sm, As, x, b, nullptr, false, CHEB_R_NONE);          // post-smoothing (same polynomial: M is symmetric)
   }
 

@@ -296,6 +296,34 @@ k_spmv_sell(int n_rows, const long long* __restrict__ slice_ptr, const float* __
     y[row] = s0 + s1;
 }
 
+// rectangular FP64 sliced-ELL product y (+)= M x (the AMG prolongator: 1..8 entries per row, thread per row)
+template <bool ACCUM>
+__global__ void __launch_bounds__(ST)
+k_spmv_sell_rect(int n_rows, const long long* __restrict__ slice_ptr, const double* __restrict__ vals,
+                 const int32_t* __restrict__ cols, const double* __restrict__ x, double* __restrict__ y)
+{
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = row >> 5, lane = row & 31;
+  if (row >= n_rows)
+    return;
+  const long long b = slice_ptr[s];
+  const int w = (int)((slice_ptr[s + 1] - b) >> 5);
+  const double* v = vals + b + lane;
+  const int32_t* c = cols + b + lane;
+  double s0 = 0.0, s1 = 0.0;
+  int k = 0;
+  for (; k + 2 <= w; k += 2)
+  {
+    const double v0 = __ldcs(v + k * SLICE), v1 = __ldcs(v + (k + 1) * SLICE);
+    const int c0 = __ldcs(c + k * SLICE), c1 = __ldcs(c + (k + 1) * SLICE);
+    s0 = fma(v0, x[c0], s0);
+    s1 = fma(v1, x[c1], s1);
+  }
+  if (k < w)
+    s0 = fma(__ldcs(v + k * SLICE), x[__ldcs(c + k * SLICE)], s0);
+  y[row] = ACCUM ? y[row] + (s0 + s1) : s0 + s1;
+}
+
 // widths[s] = 32 * max over the slice's rows of the owned-column length; overflow: a delta does not fit 16 bits
 __global__ void k_sell_widths(int n_rows, const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ off_diag,
                               const int32_t* __restrict__ cols, long long* __restrict__ widths, int* __restrict__ overflow)
@@ -370,6 +398,20 @@ k_spmv_rect(int n_rows, const double* __restrict__ vals, const int32_t* __restri
 }
 } // namespace
 
+void spmv_sell_rect(pmgx_ctx* c, int n_rows, const long long* slice_ptr, const int32_t* cols, const double* vals,
+                    const double* x, double* y, bool accumulate)
+{
+  if (n_rows <= 0)
+    return;
+  const int grid = (n_rows + ST - 1) / ST;
+  if (accumulate)
+    k_spmv_sell_rect<true><<<grid, ST, 0, c->stream>>>(n_rows, slice_ptr, vals, cols, x, y);
+  else
+    k_spmv_sell_rect<false><<<grid, ST, 0, c->stream>>>(n_rows, slice_ptr, vals, cols, x, y);
+  check_launch("k_spmv_sell_rect");
+  count_launch(c);
+}
+
 void spmv_rect(pmgx_ctx* c, int n_rows, const int32_t* row_ptr, const int32_t* cols, const double* vals,
                const double* x, double* y, bool accumulate, int lanes)
 {
@@ -400,10 +442,6 @@ void spmv_rect(pmgx_ctx* c, int n_rows, const int32_t* row_ptr, const int32_t* c
   check_launch("k_spmv_rect");
   count_launch(c);
 }
-
-namespace
-{
-} // namespace
 
 void CsrOperator::apply(double* x, double* y)
 {

@@ -84,4 +84,8 @@ int cgcg_solve(pmgx_coarse* cs, double* x, const double* b, bool x_is_zero);
 // rectangular CSR product y (=|+=) M x, `lanes` (4, 8 or 32) lanes per row (csr.cu)
 void spmv_rect(pmgx_ctx* c, int n_rows, const int32_t* row_ptr, const int32_t* cols, const double* vals,
                const double* x, double* y, bool accumulate, int lanes);
+// the same product for a matrix stored as sliced ELL (32-row slices, column-major inside a slice; padding:
+// value 0, column 0): thread per row, for short rows (the AMG prolongator)
+void spmv_sell_rect(pmgx_ctx* c, int n_rows, const long long* slice_ptr, const int32_t* cols, const double* vals,
+                    const double* x, double* y, bool accumulate);
 } // namespace pmgx
