@@ -170,6 +170,52 @@ __global__ void __launch_bounds__(256) k_zcontract_dmma(const double* __restrict
   o[r * N + 4 + q] = a1;
 }
 
+// latency / per-warp pipelining: ONE warp, NCH independent accumulator chains, `iters` dependent steps each
+template <int NCH>
+__global__ void k_dmma_latency(double* out, long long* cycles, int iters, double a, double b)
+{
+  double c0[NCH], c1[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c)
+    c0[c] = threadIdx.x * 1e-9 + c, c1[c] = c;
+  const double fa = a + threadIdx.x * 1e-12, fb = b;
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it)
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+      dmma884(c0[c], c1[c], fa, fb, c0[c], c1[c]);
+  const long long t1 = clock64();
+  double s = 0;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c)
+    s += c0[c] + c1[c];
+  out[threadIdx.x] = s;
+  if (threadIdx.x == 0)
+    *cycles = t1 - t0;
+}
+
+template <int NCH>
+__global__ void k_dfma_latency(double* out, long long* cycles, int iters, double a, double b)
+{
+  double acc[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c)
+    acc[c] = threadIdx.x * 1e-9 + c;
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it)
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+      acc[c] = fma(acc[c], a, b);
+  const long long t1 = clock64();
+  double s = 0;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c)
+    s += acc[c];
+  out[threadIdx.x] = s;
+  if (threadIdx.x == 0)
+    *cycles = t1 - t0;
+}
+
 template <typename F>
 float time_ms(F f, int reps = 5)
 {
@@ -216,6 +262,26 @@ int main(int argc, char** argv)
     float ms = time_ms([&] { k_mixed_peak<<<blocks, threads>>>(out, iters, 1.0000001, 1e-9); });
     printf("DFMA + DMMA    : %8.3f ms  %7.2f TFLOP/s (sum of both)\n", ms,
            2.0 * (CH + 8 * (CH / 2)) * iters * nthreads / ms / 1e9);
+  }
+  if (mode == 0 || mode == 6)
+  {
+    long long* cyc;
+    CK(cudaMalloc(&cyc, sizeof(long long)));
+    long long h = 0;
+    const int it = 2048;
+#define LAT(K, N)                                                                                  \
+  K<N><<<1, 32>>>(out, cyc, it, 1.0000001, 1e-9);                                                  \
+  CK(cudaMemcpy(&h, cyc, sizeof(h), cudaMemcpyDeviceToHost));                                      \
+  printf("  %-16s one warp, %d independent chain(s): %7.1f cycles per step (%.1f per instruction)\n", #K, N,       \
+         (double)h / it, (double)h / it / N);
+    printf("latency / per-warp pipelining (clock64 around a dependent loop):\n");
+    LAT(k_dfma_latency, 1)
+    LAT(k_dfma_latency, 4)
+    LAT(k_dmma_latency, 1)
+    LAT(k_dmma_latency, 2)
+    LAT(k_dmma_latency, 4)
+    LAT(k_dmma_latency, 8)
+#undef LAT
   }
   // z contraction of P7 elements
   const int ncells = sms * 2048, reps = 64;

@@ -1951,6 +1951,8 @@ void launch_apply_tma(pmgx_ctx* c, cudaStream_t st, int tpb, int r, const double
   throw Error{PMGX_ERR_ARG};
 }
 
+#include "laplacian_mma.cuh"
+
 void upload_tables(pmgx_ctx* c)
 {
   static double hD[PMGX_MAX_DEGREE + 1][MAXN * MAXN];
@@ -2002,6 +2004,7 @@ struct Laplacian : pmgx_operator
   bool affine = false; // every cell affine: k_apply_affine replaces the streamed-G kernels
   bool aff_shfl = false; // z contractions by warp shuffles instead of shared-memory rows (default for P <= 2)
   int aff_reslab = 0; // re-slabbed z direction (k_apply_affine2): 1 CTA-wide phases, 2 warp-local phases
+  bool use_mma = false; // P6 / P7 on affine cells: FP64 tensor-core kernel (k_apply_affine_mma), plain [p][n3] layout
 
   int n_list() const { return n_l + n_b; }
 
@@ -2027,9 +2030,21 @@ struct Laplacian : pmgx_operator
         halo_fwd_end(halo, x); // reference order: wait for the ghosts, then the boundary launch (:425)
     };
     bool done = false;
+    if constexpr (PP == 6 || PP == 7)
+    {
+      if (use_mma)
+      {
+        launch_apply_affine_mma<PP>(ctx, cs, x, y, Gc.p, enc.p, perm.p, kappa, 0, n_l);
+        join_before_boundary();
+        launch_apply_affine_mma<PP>(ctx, bs, x, y, Gc.p, enc.p, perm.p, kappa, n_l, n_b);
+        done = true;
+      }
+    }
     if constexpr (PP <= SLAB_MAX_DEGREE)
     {
-      if (lay.mode == 1 && affine)
+      if (done)
+        ;
+      else if (lay.mode == 1 && affine)
       {
         launch_apply_affine<PP>(ctx, cs, aff_shfl, tma_tpb, x, y, Gc.p, enc.p, perm.p, kappa, 0, 0, n_l, aff_reslab);
         join_before_boundary();
@@ -2145,9 +2160,12 @@ int pmgx_laplacian_create(pmgx_ctx* ctx, int degree, int n_cells, const int32_t*
   lay.n_l = n_lcells;
   const char* force = getenv("PMGX_APPLY_KERNEL"); // "column" forces the column kernel (A/B runs)
   lay.mode = (degree <= pmgx::SLAB_MAX_DEGREE && !(force && std::strcmp(force, "column") == 0)) ? 1 : 0;
+  // P6 / P7 on affine cells: the tensor-core kernel (PMGX_APPLY_MMA=0: the slab / column kernels)
+  const bool mma_ok = (degree == 6 || degree == 7) && !force && !(flags & PMGX_LAP_STREAM_G)
+                      && !(getenv("PMGX_APPLY_MMA") && atoi(getenv("PMGX_APPLY_MMA")) == 0);
   // affine cells: one geometry 6-vector per cell instead of one per quadrature point (decided
   // first: the batch layout follows the kernel that will run)
-  if (n_list > 0 && degree <= pmgx::SLAB_MAX_DEGREE && !force && !(flags & PMGX_LAP_STREAM_G))
+  if (n_list > 0 && (degree <= pmgx::SLAB_MAX_DEGREE || mma_ok) && !force && !(flags & PMGX_LAP_STREAM_G))
   {
     L->Gc.alloc((size_t)n_list * 6);
     pmgx::DevBuf<int> bad;
@@ -2163,6 +2181,14 @@ int pmgx_laplacian_create(pmgx_ctx* ctx, int degree, int n_cells, const int32_t*
     L->affine = n_bad == 0;
     if (!L->affine)
       L->Gc.release();
+    L->use_mma = mma_ok && L->affine;
+    if (L->use_mma)
+      lay.mode = 0; // plain enc[p][n3] / G[p][6][n3]
+    if (degree > pmgx::SLAB_MAX_DEGREE && !L->use_mma)
+    {
+      L->affine = false; // no affine kernel above the slab degrees
+      L->Gc.release();
+    }
   }
   L->use_tma = !(force && std::strcmp(force, "slab") == 0);
   L->tma_tpb = L->affine ? pmgx::affine_default_tpb(degree) : pmgx::tma_default_tpb(degree);
@@ -2267,7 +2293,9 @@ int pmgx_laplacian_kernel_name(pmgx_operator* op, char* name_h, int cap)
   PMGX_API_BEGIN
   PMGX_REQUIRE(op && op->kind == pmgx_operator::LAPLACIAN && name_h && cap > 0, "laplacian_kernel_name: bad arguments");
   auto* L = static_cast<Laplacian*>(op);
-  if (L->lay.mode == 1 && L->affine)
+  if (L->use_mma)
+    snprintf(name_h, cap, "k_apply_affine_mma<%d,2>", L->P);
+  else if (L->lay.mode == 1 && L->affine)
     snprintf(name_h, cap, "%s<%d,%d%s>", L->aff_reslab ? "k_apply_affine2" : (L->aff_shfl ? "k_apply_affine_shfl" : "k_apply_affine"),
              L->P, L->tma_tpb, L->aff_reslab == 2 ? ",warp-local" : "");
   else if (L->lay.mode == 1 && L->use_tma)
