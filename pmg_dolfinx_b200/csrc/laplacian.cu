@@ -2004,7 +2004,7 @@ struct Laplacian : pmgx_operator
   bool affine = false; // every cell affine: k_apply_affine replaces the streamed-G kernels
   bool aff_shfl = false; // z contractions by warp shuffles instead of shared-memory rows (default for P <= 2)
   int aff_reslab = 0; // re-slabbed z direction (k_apply_affine2): 1 CTA-wide phases, 2 warp-local phases
-  bool use_mma = false; // P6 / P7 on affine cells: FP64 tensor-core kernel (k_apply_affine_mma), plain [p][n3] layout
+  bool use_mma = false; // P6 / P7: FP64 tensor-core kernel (k_apply_affine_mma; G per cell if affine, else streamed), plain [p][n3] layout
 
   int n_list() const { return n_l + n_b; }
 
@@ -2034,9 +2034,15 @@ struct Laplacian : pmgx_operator
     {
       if (use_mma)
       {
-        launch_apply_affine_mma<PP>(ctx, cs, x, y, Gc.p, enc.p, perm.p, kappa, 0, n_l);
+        if (affine)
+          launch_apply_affine_mma<PP, false>(ctx, cs, x, y, Gc.p, enc.p, perm.p, kappa, 0, n_l);
+        else
+          launch_apply_affine_mma<PP, true>(ctx, cs, x, y, G.p, enc.p, perm.p, kappa, 0, n_l);
         join_before_boundary();
-        launch_apply_affine_mma<PP>(ctx, bs, x, y, Gc.p, enc.p, perm.p, kappa, n_l, n_b);
+        if (affine)
+          launch_apply_affine_mma<PP, false>(ctx, bs, x, y, Gc.p, enc.p, perm.p, kappa, n_l, n_b);
+        else
+          launch_apply_affine_mma<PP, true>(ctx, bs, x, y, G.p, enc.p, perm.p, kappa, n_l, n_b);
         done = true;
       }
     }
@@ -2160,9 +2166,13 @@ int pmgx_laplacian_create(pmgx_ctx* ctx, int degree, int n_cells, const int32_t*
   lay.n_l = n_lcells;
   const char* force = getenv("PMGX_APPLY_KERNEL"); // "column" forces the column kernel (A/B runs)
   lay.mode = (degree <= pmgx::SLAB_MAX_DEGREE && !(force && std::strcmp(force, "column") == 0)) ? 1 : 0;
-  // P6 / P7 on affine cells: the tensor-core kernel (PMGX_APPLY_MMA=0: the slab / column kernels)
-  const bool mma_ok = (degree == 6 || degree == 7) && !force && !(flags & PMGX_LAP_STREAM_G)
+  // P6 / P7: the tensor-core kernel, with G per cell on affine meshes and G streamed per quadrature point
+  // otherwise (PMGX_APPLY_MMA=0: the slab / column kernels)
+  const bool mma_ok = (degree == 6 || degree == 7) && !force
                       && !(getenv("PMGX_APPLY_MMA") && atoi(getenv("PMGX_APPLY_MMA")) == 0);
+  L->use_mma = mma_ok;
+  if (mma_ok)
+    lay.mode = 0; // plain enc[p][n3] / G[p][6][n3]
   // affine cells: one geometry 6-vector per cell instead of one per quadrature point (decided
   // first: the batch layout follows the kernel that will run)
   if (n_list > 0 && (degree <= pmgx::SLAB_MAX_DEGREE || mma_ok) && !force && !(flags & PMGX_LAP_STREAM_G))
@@ -2181,9 +2191,6 @@ int pmgx_laplacian_create(pmgx_ctx* ctx, int degree, int n_cells, const int32_t*
     L->affine = n_bad == 0;
     if (!L->affine)
       L->Gc.release();
-    L->use_mma = mma_ok && L->affine;
-    if (L->use_mma)
-      lay.mode = 0; // plain enc[p][n3] / G[p][6][n3]
     if (degree > pmgx::SLAB_MAX_DEGREE && !L->use_mma)
     {
       L->affine = false; // no affine kernel above the slab degrees
@@ -2294,7 +2301,7 @@ int pmgx_laplacian_kernel_name(pmgx_operator* op, char* name_h, int cap)
   PMGX_REQUIRE(op && op->kind == pmgx_operator::LAPLACIAN && name_h && cap > 0, "laplacian_kernel_name: bad arguments");
   auto* L = static_cast<Laplacian*>(op);
   if (L->use_mma)
-    snprintf(name_h, cap, "k_apply_affine_mma<%d,2>", L->P);
+    snprintf(name_h, cap, "k_apply_affine_mma<%d,2,%s>", L->P, L->affine ? "affine" : "streamed");
   else if (L->lay.mode == 1 && L->affine)
     snprintf(name_h, cap, "%s<%d,%d%s>", L->aff_reslab ? "k_apply_affine2" : (L->aff_shfl ? "k_apply_affine_shfl" : "k_apply_affine"),
              L->P, L->tma_tpb, L->aff_reslab == 2 ? ",warp-local" : "");

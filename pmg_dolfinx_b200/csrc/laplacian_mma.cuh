@@ -51,11 +51,15 @@ struct MmaCfg
   }
 };
 
-template <int P, int WPB, int MINB>
+// STREAM = false: Gc[p][6], one geometry 6-vector per (affine) cell, quadrature weights applied here;
+// STREAM = true : Gc = G[p][6][n3], the reference's data flow (G per quadrature point, weights folded in),
+//                 read in layout Y one tile ahead of the flux that uses it, the whole block of the NEXT cell
+//                 prefetched into L2 while this one is computed
+template <int P, int WPB, int MINB, bool STREAM>
 __global__ void __launch_bounds__(WPB * 32, MINB)
 k_apply_affine_mma(const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ Gc,
                    const int32_t* __restrict__ enc, const int32_t* __restrict__ perm,
-                   const double* __restrict__ kappa, int first, int count)
+                   const double* __restrict__ kappa, int first, int count, int prefetch)
 {
   using C = MmaCfg<P, WPB>;
   constexpr int n = C::n, n3 = C::n3, SI = C::SI;
@@ -121,9 +125,40 @@ k_apply_affine_mma(const double* __restrict__ x, double* __restrict__ y, const d
     for (int t = 0; t < n; ++t)
       *reinterpret_cast<double2*>(B0 + t * SI + yo[(t >> 1) & 1]) = make_double2(xv[t][0], xv[t][1]);
     const double kap = kappa[perm[p]]; // re-read on every apply (src/laplacian.hpp:230)
-    const double* gp = Gc + (size_t)p * 6;
-    const double G00 = gp[0] * kap, G01 = gp[1] * kap, G02 = gp[2] * kap, G11 = gp[3] * kap, G12 = gp[4] * kap,
-                 G22 = gp[5] * kap;
+    double G00 = 0, G01 = 0, G02 = 0, G11 = 0, G12 = 0, G22 = 0;
+    const double* Gq = nullptr; // STREAM: this lane's first point of the cell's G block
+    double2 gq[2][6];           // STREAM: G of the lane's two points, tiles t (flux) and t + 1 (in flight)
+    auto load_g = [&](int t, double2* g)
+    {
+#pragma unroll
+      for (int cc = 0; cc < 6; ++cc)
+      {
+        if constexpr (n == 8)
+          g[cc] = __ldcs(reinterpret_cast<const double2*>(Gq + cc * n3 + 64 * t));
+        else
+        {
+          const double* q = Gq + cc * n3 + t * n * n;
+          g[cc] = make_double2(v0 ? ldg_stream(q) : 0.0, v1 ? ldg_stream(q + 1) : 0.0);
+        }
+      }
+    };
+    if constexpr (STREAM)
+    {
+      Gq = Gc + (size_t)p * 6 * n3 + (n == 8 ? 2 * lane : r * n + 2 * c);
+      if (prefetch == 1 || (prefetch == 2 && pl + nw < count))
+      { // this (1) or the next (2) cell's block -> L2 (6 n3 doubles, 128-byte lines)
+        const uintptr_t b0 = reinterpret_cast<uintptr_t>(Gc + ((size_t)p + (prefetch == 2 ? nw : 0)) * 6 * n3),
+                        b1 = b0 + 6 * n3 * 8;
+        for (uintptr_t a = (b0 & ~(uintptr_t)127) + 128 * lane; a < b1; a += 128 * 32)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+      }
+      load_g(0, gq[0]);
+    }
+    else
+    {
+      const double* gp = Gc + (size_t)p * 6;
+      G00 = gp[0] * kap, G01 = gp[1] * kap, G02 = gp[2] * kap, G11 = gp[3] * kap, G12 = gp[4] * kap, G22 = gp[5] * kap;
+    }
     __syncwarp();
     // ---- forward contractions
     double gz[n][2], gy[n][2], gx[n][2];
@@ -150,13 +185,32 @@ k_apply_affine_mma(const double* __restrict__ x, double* __restrict__ y, const d
     {
       const int o = t * SI + yo[(t >> 1) & 1];
       const double2 g = *reinterpret_cast<const double2*>(B0 + o);
-      const double w0 = c_wts[P][t] * wr0, w1 = c_wts[P][t] * wr1;
-      *reinterpret_cast<double2*>(B0 + o) = make_double2(w0 * (G00 * g.x + G01 * gy[t][0] + G02 * gz[t][0]),
-                                                         w1 * (G00 * g.y + G01 * gy[t][1] + G02 * gz[t][1]));
-      *reinterpret_cast<double2*>(B1 + o) = make_double2(w0 * (G01 * g.x + G11 * gy[t][0] + G12 * gz[t][0]),
-                                                         w1 * (G01 * g.y + G11 * gy[t][1] + G12 * gz[t][1]));
-      *reinterpret_cast<double2*>(B2 + o) = make_double2(w0 * (G02 * g.x + G12 * gy[t][0] + G22 * gz[t][0]),
-                                                         w1 * (G02 * g.y + G12 * gy[t][1] + G22 * gz[t][1]));
+      double w0, w1;
+      if constexpr (STREAM)
+      {
+        if (t + 1 < n)
+          load_g(t + 1, gq[(t + 1) & 1]);
+        const double2* q = gq[t & 1];
+        w0 = w1 = kap;
+        G00 = q[0].x, G01 = q[1].x, G02 = q[2].x, G11 = q[3].x, G12 = q[4].x, G22 = q[5].x;
+        const double f0 = G00 * g.x + G01 * gy[t][0] + G02 * gz[t][0];
+        const double f1 = G01 * g.x + G11 * gy[t][0] + G12 * gz[t][0];
+        const double f2 = G02 * g.x + G12 * gy[t][0] + G22 * gz[t][0];
+        G00 = q[0].y, G01 = q[1].y, G02 = q[2].y, G11 = q[3].y, G12 = q[4].y, G22 = q[5].y;
+        *reinterpret_cast<double2*>(B0 + o) = make_double2(w0 * f0, w1 * (G00 * g.y + G01 * gy[t][1] + G02 * gz[t][1]));
+        *reinterpret_cast<double2*>(B1 + o) = make_double2(w0 * f1, w1 * (G01 * g.y + G11 * gy[t][1] + G12 * gz[t][1]));
+        *reinterpret_cast<double2*>(B2 + o) = make_double2(w0 * f2, w1 * (G02 * g.y + G12 * gy[t][1] + G22 * gz[t][1]));
+      }
+      else
+      {
+        w0 = c_wts[P][t] * wr0, w1 = c_wts[P][t] * wr1;
+        *reinterpret_cast<double2*>(B0 + o) = make_double2(w0 * (G00 * g.x + G01 * gy[t][0] + G02 * gz[t][0]),
+                                                           w1 * (G00 * g.y + G01 * gy[t][1] + G02 * gz[t][1]));
+        *reinterpret_cast<double2*>(B1 + o) = make_double2(w0 * (G01 * g.x + G11 * gy[t][0] + G12 * gz[t][0]),
+                                                           w1 * (G01 * g.y + G11 * gy[t][1] + G12 * gz[t][1]));
+        *reinterpret_cast<double2*>(B2 + o) = make_double2(w0 * (G02 * g.x + G12 * gy[t][0] + G22 * gz[t][0]),
+                                                           w1 * (G02 * g.y + G12 * gy[t][1] + G22 * gz[t][1]));
+      }
     }
     __syncwarp();
     // ---- transposed contractions
@@ -196,11 +250,14 @@ k_apply_affine_mma(const double* __restrict__ x, double* __restrict__ y, const d
   }
 }
 
+// CTAs of two warps per SM the kernel is compiled for.  6 (168 registers, 16 bytes of spills at P7, 12 warps per
+// SM) against 7 (128 registers, 130-180 bytes of spills, 14 warps), measured at 100 M dofs: affine P6 1.42 vs
+// 1.54 ms, P7 1.19 vs 1.38 ms; streamed P6 2.22 vs 2.93 ms, P7 1.76 vs 2.58 ms.  5 compiles to the same code as 6.
 #ifndef PMGX_MMA_MINB
 #define PMGX_MMA_MINB 6
 #endif
 
-template <int P>
+template <int P, bool STREAM>
 void launch_apply_affine_mma(pmgx_ctx* c, cudaStream_t st, const double* x, double* y, const double* Gc,
                              const int32_t* enc, const int32_t* perm, const double* kappa, int first, int count)
 {
@@ -209,15 +266,19 @@ void launch_apply_affine_mma(pmgx_ctx* c, cudaStream_t st, const double* x, doub
   constexpr int WPB = 2, MINB = PMGX_MMA_MINB;
   using C = MmaCfg<P, WPB>;
   const bool timed = c->profiling && first == 0; // per-kernel timing covers the interior-cell launch only
-  static int ctas_per_sm[64] = {0};
+  static int ctas_per_sm[64] = {0}; // per instantiation (P, STREAM)
   if (ctas_per_sm[c->device] == 0)
   {
-    PMGX_CUDA(cudaFuncSetAttribute(k_apply_affine_mma<P, WPB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem));
+    PMGX_CUDA(cudaFuncSetAttribute(k_apply_affine_mma<P, WPB, MINB, STREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem));
     int nb = 0;
-    PMGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_apply_affine_mma<P, WPB, MINB>, WPB * 32, C::smem));
+    PMGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_apply_affine_mma<P, WPB, MINB, STREAM>, WPB * 32, C::smem));
     PMGX_REQUIRE(nb >= 1, "k_apply_affine_mma<%d> does not fit on an SM", P);
     ctas_per_sm[c->device] = nb;
   }
+  // L2 prefetch of the streamed G block, measured at 100 M dofs (none / this cell / next cell): P6 2.36 / 2.22 /
+  // 2.23 ms, P7 1.76 / 1.85 / 2.19 ms (at n = 8 the 16-byte tile loads stream well on their own and the prefetch
+  // only adds DRAM traffic: 12.3 GB against 9.3 GB algorithmic, profiles/r2_apply_p7_mma.txt)
+  static const int prefetch = getenv("PMGX_MMA_PREFETCH") ? atoi(getenv("PMGX_MMA_PREFETCH")) : (P == 7 ? 0 : 1);
   const int grid = std::min((count + WPB - 1) / WPB, ctas_per_sm[c->device] * c->num_sms);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (timed)
@@ -226,7 +287,7 @@ void launch_apply_affine_mma(pmgx_ctx* c, cudaStream_t st, const double* x, doub
     PMGX_CUDA(cudaEventCreate(&e1));
     PMGX_CUDA(cudaEventRecord(e0, st));
   }
-  k_apply_affine_mma<P, WPB, MINB><<<grid, WPB * 32, C::smem, st>>>(x, y, Gc, enc, perm, kappa, first, count);
+  k_apply_affine_mma<P, WPB, MINB, STREAM><<<grid, WPB * 32, C::smem, st>>>(x, y, Gc, enc, perm, kappa, first, count, prefetch);
   check_launch("k_apply_affine_mma");
   count_launch(c);
   if (timed)

@@ -41,5 +41,6 @@ def run(P, ndofs, reps=10, perturb=0.0):
 if __name__ == "__main__":
     nd = int(float(sys.argv[1])) if len(sys.argv) > 1 else 100_000_000
     degs = [int(a) for a in sys.argv[2].split(",")] if len(sys.argv) > 2 else [3]
+    perturb = float(sys.argv[3]) if len(sys.argv) > 3 else 0.0   # > 0: non-affine cells, G streamed
     for P in degs:
-        run(P, nd)
+        run(P, nd, perturb=perturb)
