@@ -89,17 +89,10 @@ k_apply_affine_mma(const double* __restrict__ x, double* __restrict__ y, const d
   const bool v0 = r < n && 2 * c < n, v1 = r < n && 2 * c + 1 < n; // the lane's two points exist (n = 7 pads)
 
   const int gw = blockIdx.x * WPB + warp, nw = gridDim.x * WPB;
-  for (int pl = gw; pl < count; pl += nw)
+  // this lane's dof indices of cell pl (layout Y), -1 where the lane has no point
+  auto load_idx = [&](int pl, int32_t (*d)[2])
   {
-    const long long p = (long long)first + pl;
-    const int32_t* e = enc + p * n3;
-    int32_t d[n][2];
-    double xv[n][2];
-    // gather (Dirichlet columns zeroed: src/laplacian.hpp:186-187) in sweeps -- all index loads, then all value
-    // loads -- so that every lane has 2 n loads in flight per sweep.  No global store may sit between the
-    // loads: with the Dirichlet-row stores y = x in this loop (as in the slab kernels) every index -> value ->
-    // store chain was exposed at full latency, even with the store predicated off (ncu: long_scoreboard 28.7
-    // stalls per issue, 4.4 ms instead of 1.2 ms at P7); they are done in the scatter, under a branch.
+    const int32_t* e = enc + ((long long)first + pl) * n3;
 #pragma unroll
     for (int t = 0; t < n; ++t)
     {
@@ -116,6 +109,20 @@ k_apply_affine_mma(const double* __restrict__ x, double* __restrict__ y, const d
         d[t][1] = v1 ? ldg_stream_i32(e + a + 1) : -1;
       }
     }
+  };
+  int32_t d[n][2], dn[n][2];
+  if (gw < count)
+    load_idx(gw, d);
+  for (int pl = gw; pl < count; pl += nw)
+  {
+    const long long p = (long long)first + pl;
+    double xv[n][2];
+    // gather (Dirichlet columns zeroed: src/laplacian.hpp:186-187): all value loads in one sweep, the indices were
+    // loaded one cell ahead (below, before the transposed contractions), so one global round trip per cell is
+    // exposed instead of two.  No global store may sit between the loads: with the Dirichlet-row stores y = x in
+    // this loop (as in the slab kernels) every index -> value -> store chain was exposed at full latency, even
+    // with the store predicated off (ncu: long_scoreboard 28.7 stalls per issue, 4.4 ms instead of 1.2 ms at
+    // P7); they are done in the scatter, under a branch.
 #pragma unroll
     for (int t = 0; t < n; ++t)
 #pragma unroll
@@ -213,6 +220,8 @@ k_apply_affine_mma(const double* __restrict__ x, double* __restrict__ y, const d
       }
     }
     __syncwarp();
+    if (pl + nw < count)
+      load_idx(pl + nw, dn); // the forward accumulators are dead: registers for the next cell's indices
     // ---- transposed contractions
     double ayz[n][2], ax[n][2];
 #pragma unroll
@@ -247,6 +256,9 @@ k_apply_affine_mma(const double* __restrict__ x, double* __restrict__ y, const d
       }
     }
     // no barrier here: B1 is next written by the flux phase, three barriers into the next cell
+#pragma unroll
+    for (int t = 0; t < n; ++t)
+      d[t][0] = dn[t][0], d[t][1] = dn[t][1];
   }
 }
 
