@@ -110,16 +110,22 @@ k_apply_affine_mma(const double* __restrict__ x, double* __restrict__ y, const d
       }
     }
   };
+  // STREAM: the indices are loaded one cell ahead (before the transposed contractions, when the forward
+  // accumulators are dead), so one global round trip of the gather is exposed per cell instead of two.  Measured
+  // at 100 M dofs, ahead vs not: streamed P6 2.13 vs 2.22 ms, P7 1.74 vs 1.76 ms; affine P6 1.55 vs 1.42 ms,
+  // P7 1.21 vs 1.20 ms (there the 16 extra live registers cost more than the round trip: 88 bytes of spills)
+  constexpr bool AHEAD = STREAM;
   int32_t d[n][2], dn[n][2];
-  if (gw < count)
+  if (AHEAD && gw < count)
     load_idx(gw, d);
   for (int pl = gw; pl < count; pl += nw)
   {
     const long long p = (long long)first + pl;
     double xv[n][2];
-    // gather (Dirichlet columns zeroed: src/laplacian.hpp:186-187): all value loads in one sweep, the indices were
-    // loaded one cell ahead (below, before the transposed contractions), so one global round trip per cell is
-    // exposed instead of two.  No global store may sit between the loads: with the Dirichlet-row stores y = x in
+    if constexpr (!AHEAD)
+      load_idx(pl, d);
+    // gather (Dirichlet columns zeroed: src/laplacian.hpp:186-187): all index loads in one sweep (above, or one
+    // cell ahead), all value loads in the next.  No global store may sit between the loads: with the Dirichlet-row stores y = x in
     // this loop (as in the slab kernels) every index -> value -> store chain was exposed at full latency, even
     // with the store predicated off (ncu: long_scoreboard 28.7 stalls per issue, 4.4 ms instead of 1.2 ms at
     // P7); they are done in the scatter, under a branch.
@@ -220,8 +226,9 @@ k_apply_affine_mma(const double* __restrict__ x, double* __restrict__ y, const d
       }
     }
     __syncwarp();
-    if (pl + nw < count)
-      load_idx(pl + nw, dn); // the forward accumulators are dead: registers for the next cell's indices
+    if constexpr (AHEAD)
+      if (pl + nw < count)
+        load_idx(pl + nw, dn);
     // ---- transposed contractions
     double ayz[n][2], ax[n][2];
 #pragma unroll
@@ -256,9 +263,12 @@ k_apply_affine_mma(const double* __restrict__ x, double* __restrict__ y, const d
       }
     }
     // no barrier here: B1 is next written by the flux phase, three barriers into the next cell
+    if constexpr (AHEAD)
+    {
 #pragma unroll
-    for (int t = 0; t < n; ++t)
-      d[t][0] = dn[t][0], d[t][1] = dn[t][1];
+      for (int t = 0; t < n; ++t)
+        d[t][0] = dn[t][0], d[t][1] = dn[t][1];
+    }
   }
 }
 
