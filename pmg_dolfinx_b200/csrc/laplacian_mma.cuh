@@ -125,10 +125,10 @@ k_apply_affine_mma(const double* __restrict__ x, double* __restrict__ y, const d
     if constexpr (!AHEAD)
       load_idx(pl, d);
     // gather (Dirichlet columns zeroed: src/laplacian.hpp:186-187): all index loads in one sweep (above, or one
-    // cell ahead), all value loads in the next.  No global store may sit between the loads: with the Dirichlet-row stores y = x in
-    // this loop (as in the slab kernels) every index -> value -> store chain was exposed at full latency, even
-    // with the store predicated off (ncu: long_scoreboard 28.7 stalls per issue, 4.4 ms instead of 1.2 ms at
-    // P7); they are done in the scatter, under a branch.
+    // cell ahead), all value loads in the next.  No global store may sit between the loads: with the
+    // Dirichlet-row stores y = x in this loop (as in the slab kernels) every index -> value -> store chain was
+    // exposed at full latency, even with the store predicated off (ncu: long_scoreboard 28.7 stalls per issue,
+    // 4.4 ms instead of 1.2 ms at P7); they are done in the scatter, under a branch.
 #pragma unroll
     for (int t = 0; t < n; ++t)
 #pragma unroll
