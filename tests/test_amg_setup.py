@@ -76,3 +76,18 @@ def test_setup_rejects_bad_input():
     ix = np.array([0, 1], dtype=np.int32)
     v = np.array([1.0, -2.0])                      # non-positive diagonal
     assert lib.pmgx_amg_setup_h(2, ptr(ip), ptr(ix), ptr(v), 0, 4, ctypes.addressof(h)) != 0
+
+
+def test_setup_degenerate_sizes():
+    """1 x 1, the identity (every row a Dirichlet row) and a Laplacian with identity rows appended: the set-up
+    returns a hierarchy (a single level where there is nothing to coarsen) instead of failing."""
+    import scipy.sparse as sp
+    T = sp.diags([-1.0, 2.0, -1.0], [-1, 0, 1], shape=(100, 100))
+    for A, min_levels in ((sp.eye(1) * 2.0, 1), (sp.eye(50), 1), (sp.block_diag([T, sp.eye(30)]), 2)):
+        A = sp.csr_matrix(A)
+        A.sort_indices()
+        ip, ix = A.indptr.astype(np.int32), A.indices.astype(np.int32)
+        h = ctypes.c_void_p()
+        check(lib.pmgx_amg_setup_h(A.shape[0], ptr(ip), ptr(ix), ptr(A.data), 4, 10, ctypes.addressof(h)))
+        assert lib.pmgx_amg_num_levels(h) >= min_levels
+        lib.pmgx_amg_destroy(h)

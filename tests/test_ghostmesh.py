@@ -140,3 +140,23 @@ def test_ghostmesh_rejects_bad_input():
     assert lib.pmgx_ghostmesh_create(0, 1, 1, ptr(cells), ptr(owner), 7, ptr(xs), ctypes.addressof(h)) != 0  # vertex id 7 >= 7
     owner[0] = 3
     assert lib.pmgx_ghostmesh_create(0, 2, 1, ptr(cells), ptr(owner), 8, ptr(xs), ctypes.addressof(h)) != 0  # owner out of range
+
+
+def test_ghostmesh_ranks_without_cells():
+    """A partition may leave ranks empty (more ranks than parts): they get empty arrays and the global dof count,
+    the rank that owns everything gets the single-domain arrays with no ghosts."""
+    from pmg_dolfinx_b200 import api
+    m = om.create_box(2, 2, 2)
+    cv = m.geom_dofmap.astype(np.int64)
+    owner = np.zeros(len(cv), dtype=np.int32)
+    for rank in range(3):
+        gm = api.GhostLayerMesh(cv, owner, m.verts, rank, 3)
+        sp = gm.space(2)
+        assert sp.n_global == 125
+        if rank == 0:
+            assert (gm.n_cells, gm.n_owned_cells, sp.n_owned, sp.n_ghost) == (8, 8, 125, 0)
+            assert len(gm.lcells) == 8 and len(gm.bcells) == 0 and len(sp.send_ranks) == 0 and len(sp.recv_ranks) == 0
+        else:
+            assert (gm.n_cells, gm.n_owned_cells, sp.n_owned, sp.n_ghost) == (0, 0, 0, 0)
+            assert len(gm.lcells) == 0 and len(gm.bcells) == 0
+        gm.close()
