@@ -6,7 +6,9 @@ directions only through swizzled shared-memory arrays.  This test runs exactly t
 32 "lanes" as array elements, the mma as a small matrix product in the documented layout, the same swizzled
 addresses (and a count of the shared-memory bank conflicts of every access) --
 on a sheared (affine) cell against the oracle, so that an indexing error shows up without a GPU.  The CUDA
-kernel itself is checked against the oracle by tests/test_gpu_operator.py (P6, P7 on affine meshes)."""
+kernel itself is checked against the oracle by tests/test_gpu_operator.py (P6, P7 on affine and perturbed meshes).
+The second test restates the streamed-G variant as one warp of a launch runs it (cell loop, Dirichlet handling,
+G in layout Y, dof indices one cell ahead) and drives a whole mesh through it."""
 import numpy as np
 import pytest
 
@@ -60,17 +62,12 @@ def mma(a, b, c0, c1):
     return c0 + C[lane // 4, 2 * (lane % 4)], c1 + C[lane // 4, 2 * (lane % 4) + 1]
 
 
-def apply_cell(P, u_cell, Gc, kappa):
-    """u_cell[n,n,n] (BC already zeroed) -> acc[n,n,n]"""
+def _contract_cell(P, B0, B1, B2, flux):
+    """forward contractions, re-layout of gx, flux(t, gx, gy, gz) -> (fx, fy, fz) pairs at the Y points, transposed
+    contractions, re-layout of the X accumulator; U is in B0 on entry; returns the Y-layout result [t][e][lane]"""
     n = P + 1
-    x1, w1, D1 = gll.tables(P)            # D1[q, i] = l_i'(x_q)
+    _, _, D1 = gll.tables(P)              # D1[q, i] = l_i'(x_q)
     D = np.zeros((8, 8)); D[:n, :n] = D1
-    w = np.zeros(8); w[:n] = w1
-    B0 = np.zeros(8 * SI); B1 = np.zeros(8 * SI); B2 = np.zeros(8 * SI)
-    up = np.zeros((8, 8, 8)); up[:n, :n, :n] = u_cell
-    # gather in layout Y: lane (r, c) holds (t, r, 2c), (t, r, 2c + 1)
-    for t in range(n):
-        sts2(B0, at(t, r, 2 * c), up[t, r, 2 * c], up[t, r, 2 * c + 1])
     dA0, dA1 = D[r, c], D[r, c + 4]            # A = D (x, y forward); also B = D^T (z forward)
     tA0, tA1 = D[c, r], D[c + 4, r]            # A = D^T (x, y backward); also B = D (z backward)
     gz = np.zeros((8, 2, 32)); gy = np.zeros((8, 2, 32)); gx = np.zeros((8, 2, 32))
@@ -84,20 +81,12 @@ def apply_cell(P, u_cell, Gc, kappa):
         gx[t] = mma(dA1, lds(B0, at(c + 4, t, r)), c0, c1)
     for t in range(n):                                                  # gx: layout X -> shared memory
         sts2(B0, at(r, t, 2 * c), gx[t, 0], gx[t, 1])
-    G00, G01, G02, G11, G12, G22 = Gc
     for t in range(n):                                                  # flux at the Y points
         o = at(t, r, 2 * c)
-        g0, g1 = lds2(B0, o)
-        gxy = (g0, g1)
-        f = np.zeros((3, 2, 32))
-        for e in range(2):
-            ww = kappa * w[t] * w[r] * w[2 * c + e]
-            f[0, e] = ww * (G00 * gxy[e] + G01 * gy[t, e] + G02 * gz[t, e])
-            f[1, e] = ww * (G01 * gxy[e] + G11 * gy[t, e] + G12 * gz[t, e])
-            f[2, e] = ww * (G02 * gxy[e] + G12 * gy[t, e] + G22 * gz[t, e])
-        sts2(B0, o, f[0, 0], f[0, 1])
-        sts2(B1, o, f[1, 0], f[1, 1])
-        sts2(B2, o, f[2, 0], f[2, 1])
+        f = flux(t, lds2(B0, o), gy[t], gz[t])
+        sts2(B0, o, f[0][0], f[0][1])
+        sts2(B1, o, f[1][0], f[1][1])
+        sts2(B2, o, f[2][0], f[2][1])
     ayz = np.zeros((8, 2, 32)); ax = np.zeros((8, 2, 32))
     for t in range(n):
         c0, c1 = mma(lds(B2, at(t, r, c)), tA0, z0, z0)                 # z': A[j][q'] = fz[t][j][q'], B = D
@@ -108,13 +97,92 @@ def apply_cell(P, u_cell, Gc, kappa):
         ax[t] = mma(tA1, lds(B0, at(c + 4, t, r)), d0, d1)
     for t in range(n):
         sts2(B1, at(r, t, 2 * c), ax[t, 0], ax[t, 1])
-    acc = np.zeros((8, 8, 8))
+    out = np.zeros((8, 2, 32))
     for t in range(n):
         a0, a1 = lds2(B1, at(t, r, 2 * c))
-        acc[t, r, 2 * c] = ayz[t, 0] + a0
-        acc[t, r, 2 * c + 1] = ayz[t, 1] + a1
+        out[t, 0], out[t, 1] = ayz[t, 0] + a0, ayz[t, 1] + a1
+    return out
+
+
+def apply_cell(P, u_cell, Gc, kappa):
+    """affine variant on one cell: u_cell[n,n,n] (BC already zeroed) -> acc[n,n,n]"""
+    n = P + 1
+    _, w1, _ = gll.tables(P)
+    w = np.zeros(8); w[:n] = w1
+    B0 = np.zeros(8 * SI); B1 = np.zeros(8 * SI); B2 = np.zeros(8 * SI)
+    up = np.zeros((8, 8, 8)); up[:n, :n, :n] = u_cell
+    for t in range(n):                    # gather in layout Y: lane (r, c) holds (t, r, 2c), (t, r, 2c + 1)
+        sts2(B0, at(t, r, 2 * c), up[t, r, 2 * c], up[t, r, 2 * c + 1])
+    G00, G01, G02, G11, G12, G22 = Gc
+
+    def flux(t, gxy, gy, gz):
+        f = np.zeros((3, 2, 32))
+        for e in range(2):
+            ww = kappa * w[t] * w[r] * w[2 * c + e]
+            f[0, e] = ww * (G00 * gxy[e] + G01 * gy[e] + G02 * gz[e])
+            f[1, e] = ww * (G01 * gxy[e] + G11 * gy[e] + G12 * gz[e])
+            f[2, e] = ww * (G02 * gxy[e] + G12 * gy[e] + G22 * gz[e])
+        return f
+
+    res = _contract_cell(P, B0, B1, B2, flux)
+    acc = np.zeros((8, 8, 8))
+    for t in range(n):
+        acc[t, r, 2 * c] = res[t, 0]
+        acc[t, r, 2 * c + 1] = res[t, 1]
     assert np.all(acc[n:] == 0) and np.all(acc[:, n:] == 0) and np.all(acc[:, :, n:] == 0)
     return acc[:n, :n, :n]
+
+
+def warp_kernel(P, enc, G, kappa, x, y, first, count, gw, nw, ahead):
+    """streamed-G variant as ONE warp of the launch runs it: the cell loop with stride nw, dof indices loaded in
+    layout Y (one cell ahead if `ahead`), Dirichlet columns zeroed in the gather, G[p][6][n3] read in layout Y
+    tile by tile, atomics / Dirichlet rows in the scatter.  enc, G flat as on the device."""
+    n = P + 1
+    n3 = n ** 3
+    v = [(r < n) & (2 * c + e < n) for e in range(2)]          # the lane's two points exist (n = 7 pads)
+
+    def load_idx(pl):
+        e0 = (first + pl) * n3
+        d = -np.ones((8, 2, 32), dtype=np.int64)
+        for t in range(n):
+            a = t * n * n + r * n + 2 * c                       # n = 8: 64 t + 2 lane, the linear order
+            for e in range(2):
+                d[t, e, v[e]] = enc[e0 + a[v[e]] + e]
+        return d
+
+    B0 = np.zeros(8 * SI); B1 = np.zeros(8 * SI); B2 = np.zeros(8 * SI)
+    d = load_idx(gw) if ahead and gw < count else None
+    for pl in range(gw, count, nw):
+        p = first + pl
+        if not ahead:
+            d = load_idx(pl)
+        for t in range(n):
+            xv = [np.where(d[t, e] >= 0, x[np.maximum(d[t, e], 0)], 0.0) for e in range(2)]
+            sts2(B0, at(t, r, 2 * c), xv[0], xv[1])
+        Gq = p * 6 * n3 + r * n + 2 * c
+
+        def flux(t, gxy, gy, gz):
+            g = np.zeros((6, 2, 32))
+            for cc in range(6):
+                for e in range(2):
+                    g[cc, e, v[e]] = G[Gq[v[e]] + cc * n3 + t * n * n + e]
+            f = np.zeros((3, 2, 32))
+            for e in range(2):
+                f[0, e] = kappa[p] * (g[0, e] * gxy[e] + g[1, e] * gy[e] + g[2, e] * gz[e])
+                f[1, e] = kappa[p] * (g[1, e] * gxy[e] + g[3, e] * gy[e] + g[4, e] * gz[e])
+                f[2, e] = kappa[p] * (g[2, e] * gxy[e] + g[4, e] * gy[e] + g[5, e] * gz[e])
+            return f
+
+        res = _contract_cell(P, B0, B1, B2, flux)
+        dn = load_idx(pl + nw) if ahead and pl + nw < count else None
+        for t in range(n):
+            for e in range(2):
+                add = d[t, e] >= 0
+                np.add.at(y, d[t, e][add], res[t, e][add])
+                row = (d[t, e] < 0) & v[e]                      # Dirichlet row: y = x
+                y[~d[t, e][row]] = x[~d[t, e][row]]
+        if ahead:
+            d = dn
 
 
 @pytest.mark.parametrize("P", [7, 6, 4, 2])
@@ -139,3 +207,26 @@ def test_lane_level_mma_apply_matches_oracle(P):
     assert np.linalg.norm(y - yo) <= 1e-13 * np.linalg.norm(yo)
     # the swizzled layout is bank-conflict free for every access of the kernel
     assert WAVEFRONTS["actual"] == WAVEFRONTS["ideal"], WAVEFRONTS
+
+
+@pytest.mark.parametrize("P,ahead", [(7, True), (6, True), (6, False), (3, True)])
+def test_lane_level_streamed_kernel_on_a_mesh(P, ahead):
+    """The streamed-G variant as the launch runs it: a perturbed 2x3x2 box with its Dirichlet boundary, an interior
+    and a boundary launch (first / count), three "warps" sharing the cells so that each loops over several cells
+    (the small GPU parity meshes give every warp at most one cell), dof indices one cell ahead or not."""
+    m = om.create_box(2, 3, 2, perturb=0.2)
+    n3 = (P + 1) ** 3
+    dm, bc, nd = om.dofmap(m, P), om.bc_marker(m, P), om.num_dofs(m, P)
+    G, _ = oo.geometry_factors(m.verts, m.geom_dofmap, P)
+    kap = np.random.default_rng(5).uniform(0.5, 2.0, m.ncells)
+    x = np.random.default_rng(1).uniform(-1, 1, nd)
+    yo = oo.apply(P, dm, G, kap, bc, x)
+    enc = np.where(bc[dm] != 0, ~dm.astype(np.int64), dm.astype(np.int64)).reshape(-1)     # enc = bc[d] ? ~d : d
+    Gdev = np.ascontiguousarray(np.transpose(G, (0, 2, 1))).reshape(-1)                    # G[p][6][n3]
+    assert enc.size == m.ncells * n3 and Gdev.size == m.ncells * 6 * n3
+    y = np.zeros(nd)
+    n_l = 7                                                                               # "interior" launch, then the rest
+    for first, count in ((0, n_l), (n_l, m.ncells - n_l)):
+        for gw in range(3):
+            warp_kernel(P, enc, Gdev, kap, x, y, first, count, gw, 3, ahead)
+    assert np.linalg.norm(y - yo) <= 1e-12 * np.linalg.norm(yo)
