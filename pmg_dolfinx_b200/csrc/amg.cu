@@ -305,6 +305,21 @@ int pmgx_coarse_create_amg(pmgx_ctx* ctx, pmgx_operator* A, int max_iter, double
         A0.cols[A0.ptr[i] + t] = row[t].first, A0.vals[A0.ptr[i] + t] = row[t].second;
     }
   }
+  // Stored zeros: the device assembly keeps the full pattern of the element matrices (27 entries per row at P1),
+  // of which 7 (affine boxes, collocated quadrature) to 19 are non-zero.  The set-up below gets the pattern (its
+  // aggregates follow it: 3 x 3 x 3 blocks); the SpMVs of the solve -- PCG and the level-0 smoother, the only ones
+  // that stream from HBM -- can run on a copy without the zeros: the same sums minus exact-zero products.
+  // Opt-in (PMGX_AMG_DROP_ZEROS=1): written after the round's GPU budget was spent, so only its host part is
+  // tested (tests/test_amg_setup.py) and its effect is a prediction, not a measurement.
+  pmgx::amg::Csr Az;
+  if (getenv("PMGX_AMG_DROP_ZEROS") && atoi(getenv("PMGX_AMG_DROP_ZEROS")) == 1 && Ac->n_owned > 0)
+  {
+    A0.n_rows = Ac->n_owned;
+    A0.n_cols = Ac->n_owned + Ac->n_ghost;
+    Az = pmgx::amg::drop_stored_zeros(A0);
+    if (Az.nnz() * 5 > A0.nnz() * 4) // less than a fifth to gain: not worth a second copy
+      Az = pmgx::amg::Csr();
+  }
   const pmgx::amg::Plan plan0 = pmgx::plan_of(Ac->halo);
   pmgx::amg::Comm cm;
   cm.rank = ctx->rank;
@@ -349,6 +364,24 @@ int pmgx_coarse_create_amg(pmgx_ctx* ctx, pmgx_operator* A, int max_iter, double
     {
       D.A = A; // the caller's operator and halo
       D.halo_v = Ac->halo;
+      if (!Az.ptr.empty())
+      { // ... or its copy without the stored zeros (same halo, same vectors)
+        std::vector<int32_t> off((size_t)Ac->n_owned);
+        for (int i = 0; i < Ac->n_owned; ++i)
+        {
+          int32_t j = Az.ptr[i];
+          while (j < Az.ptr[i + 1] && Az.cols[j] < Ac->n_owned)
+            ++j;
+          off[i] = j;
+        }
+        pmgx_operator* Acmp = nullptr;
+        const int rc = pmgx_csr_create(ctx, Ac->n_owned, Ac->n_ghost, Az.ptr.data(), off.data(), Az.cols.data(),
+                                       Az.vals.data(), Ac->halo, &Acmp);
+        if (rc != PMGX_OK)
+          return rc;
+        D.A = Acmp;
+        D.own_A = true;
+      }
     }
     else
     {
@@ -399,7 +432,7 @@ int pmgx_coarse_create_amg(pmgx_ctx* ctx, pmgx_operator* A, int max_iter, double
     // level 0 is the only level that does not fit the L2: its smoother streams the matrix with FP32
     // values and 16-bit column deltas (PMGX_AMG_LP=0: the FP64 matrix)
     if (l == 0 && !last && use_lp)
-      D.A_lp = pmgx::make_lp(Ac);
+      D.A_lp = pmgx::make_lp(static_cast<pmgx::CsrOperator*>(D.A));
     D.nnz_p = L.P.nnz();
     if (!last)
     {
@@ -423,7 +456,7 @@ int pmgx_coarse_create_amg(pmgx_ctx* ctx, pmgx_operator* A, int max_iter, double
   PMGX_CUDA(cudaStreamSynchronize(ctx->stream));
 
   pmgx_coarse* cs = nullptr;
-  const int rc = pmgx_coarse_create(ctx, A, max_iter, rtol, &cs);
+  const int rc = pmgx_coarse_create(ctx, M->lv[0].A, max_iter, rtol, &cs); // PCG on the matrix without stored zeros too
   if (rc != PMGX_OK)
     return rc;
   cs->M = M.release();

@@ -78,6 +78,11 @@ struct Hierarchy
   std::vector<Level> levels;
 };
 
+// A without its stored zeros (the diagonal entry of a row is kept whatever its value).  The device assembly keeps
+// the full pattern of the element matrices (27 entries per row at P1) of which 7 (affine boxes) to 19 are non-zero:
+// the set-up wants that pattern (its aggregates follow it), the SpMVs of the solve do not.
+Csr drop_stored_zeros(const Csr& A);
+
 // collective; A0's columns >= n_owned address the ghosts of plan0
 void setup(Hierarchy& H, Csr A0, int n_owned, int n_ghost, const Plan& plan0, const Comm& comm, int min_coarse,
            int max_levels);

@@ -461,6 +461,36 @@ void check_plan(const Plan& p, int n_owned, int n_ghost)
 }
 } // namespace
 
+
+Csr drop_stored_zeros(const Csr& A)
+{
+  Csr B;
+  B.n_rows = A.n_rows;
+  B.n_cols = A.n_cols;
+  B.ptr.assign((size_t)A.n_rows + 1, 0);
+  for (int i = 0; i < A.n_rows; ++i)
+  {
+    int32_t kept = 0;
+    for (int32_t j = A.ptr[i]; j < A.ptr[i + 1]; ++j)
+      kept += (A.vals[j] != 0.0 || A.cols[j] == i) ? 1 : 0;
+    B.ptr[(size_t)i + 1] = B.ptr[i] + kept;
+  }
+  B.cols.resize((size_t)B.ptr[A.n_rows]);
+  B.vals.resize((size_t)B.ptr[A.n_rows]);
+  for (int i = 0; i < A.n_rows; ++i)
+  {
+    int32_t o = B.ptr[i];
+    for (int32_t j = A.ptr[i]; j < A.ptr[i + 1]; ++j)
+      if (A.vals[j] != 0.0 || A.cols[j] == i)
+      {
+        B.cols[o] = A.cols[j];
+        B.vals[o] = A.vals[j];
+        ++o;
+      }
+  }
+  return B;
+}
+
 void setup(Hierarchy& H, Csr A0, int n_owned, int n_ghost, const Plan& plan0, const Comm& cm, int min_coarse,
            int max_levels)
 {
@@ -1028,6 +1058,27 @@ int pmgx_amg_setup_h(int n_rows, const int32_t* row_ptr_h, const int32_t* cols_h
 {
   return pmgx_amg_setup_dist_h(0, 1, n_rows, 0, row_ptr_h, cols_h, values_h, 0, nullptr, nullptr, nullptr, 0, nullptr,
                                nullptr, nullptr, nullptr, nullptr, min_coarse, max_levels, out);
+}
+
+int pmgx_csr_drop_zeros_h(int n_rows, const int32_t* ptr_h, const int32_t* cols_h, const double* vals_h,
+                          int32_t* out_ptr_h, int32_t* out_cols_h, double* out_vals_h, long long* kept_h)
+{
+  PMGX_API_BEGIN
+  PMGX_REQUIRE(n_rows >= 0 && ptr_h && kept_h && (ptr_h[n_rows] == 0 || (cols_h && vals_h)), "csr_drop_zeros: bad arguments");
+  pmgx::amg::Csr A;
+  A.n_rows = A.n_cols = n_rows;
+  A.ptr.assign(ptr_h, ptr_h + n_rows + 1);
+  A.cols.assign(cols_h, cols_h + ptr_h[n_rows]);
+  A.vals.assign(vals_h, vals_h + ptr_h[n_rows]);
+  const pmgx::amg::Csr B = pmgx::amg::drop_stored_zeros(A);
+  *kept_h = B.nnz();
+  if (out_ptr_h)
+    std::copy(B.ptr.begin(), B.ptr.end(), out_ptr_h);
+  if (out_cols_h)
+    std::copy(B.cols.begin(), B.cols.end(), out_cols_h);
+  if (out_vals_h)
+    std::copy(B.vals.begin(), B.vals.end(), out_vals_h);
+  PMGX_API_END
 }
 
 int pmgx_amg_num_levels(pmgx_amg_hier* h) { return h ? (int)h->H.levels.size() : -1; }

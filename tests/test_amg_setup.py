@@ -91,3 +91,35 @@ def test_setup_degenerate_sizes():
         check(lib.pmgx_amg_setup_h(A.shape[0], ptr(ip), ptr(ix), ptr(A.data), 4, 10, ctypes.addressof(h)))
         assert lib.pmgx_amg_num_levels(h) >= min_levels
         lib.pmgx_amg_destroy(h)
+
+
+def test_drop_stored_zeros():
+    """pmgx_csr_drop_zeros_h: what the AMG coarse solver streams instead of the assembled pattern -- equal to scipy's
+    eliminate_zeros except that a zero DIAGONAL entry stays; row order and entry order are preserved."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(11)
+    n = 200
+    A = sp.random(n, n, density=0.05, random_state=3, format="lil")
+    A.setdiag(rng.uniform(1, 2, n))
+    A = sp.csr_matrix(A)
+    A.sort_indices()
+    zero = rng.random(A.nnz) < 0.6
+    A.data[zero] = 0.0                                    # explicit zeros, some of them on the diagonal
+    ip, ix = A.indptr.astype(np.int32), A.indices.astype(np.int32)
+    kept = ctypes.c_longlong(0)
+    check(lib.pmgx_csr_drop_zeros_h(n, ptr(ip), ptr(ix), ptr(A.data), None, None, None, ctypes.addressof(kept)))
+    rows = np.repeat(np.arange(n), np.diff(ip))
+    keep = (A.data != 0.0) | (ix == rows)
+    assert kept.value == int(keep.sum()) < A.nnz
+    op, oc, ov = np.zeros(n + 1, np.int32), np.zeros(kept.value, np.int32), np.zeros(kept.value)
+    check(lib.pmgx_csr_drop_zeros_h(n, ptr(ip), ptr(ix), ptr(A.data), ptr(op), ptr(oc), ptr(ov), ctypes.addressof(kept)))
+    assert np.array_equal(op, np.concatenate([[0], np.cumsum(np.bincount(rows[keep], minlength=n))]))
+    assert np.array_equal(oc, ix[keep]) and np.array_equal(ov, A.data[keep])
+    B = sp.csr_matrix((ov, oc, op), shape=(n, n))
+    x = rng.uniform(-1, 1, n)
+    assert np.array_equal(B @ x, A @ x) or np.allclose(B @ x, A @ x, rtol=1e-15, atol=0)
+    assert np.all(B.diagonal() == A.diagonal()) and all(i in oc[op[i]:op[i + 1]] for i in range(n))
+    # an empty matrix
+    z = np.zeros(1, np.int32)
+    check(lib.pmgx_csr_drop_zeros_h(0, ptr(z), None, None, None, None, None, ctypes.addressof(kept)))
+    assert kept.value == 0
